@@ -1,0 +1,229 @@
+"""GPU (B200): the CUDA path, called through the C ABI (ctypes via vlg_b200.ops), against the
+CPU oracle and the committed reference goldens on identical inputs and decoder draws.
+
+Tolerances (north_star): fp32 variant <= 1e-4 relative per-step energy; the tests assert a much
+tighter bound where the arithmetic allows it and say so."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import geodesic_oracle as O
+from tests import helpers as Hh
+
+pytestmark = pytest.mark.gpu
+
+FP32_STEP_TOL = 1e-4  # north_star: relative per-step energy, fp32 variant
+
+
+@pytest.fixture(scope="module")
+def vlg(built_lib):
+    import vlg_b200
+    assert torch.cuda.is_available(), "GPU tests need a B200"
+    return vlg_b200
+
+
+def make_model(vlg, g, dev="cuda"):
+    return vlg.GeodesicSplineBatch(torch.tensor(g["a"], device=dev), torch.tensor(g["b"], device=dev),
+                                   torch.tensor(g["basis"], device=dev), torch.tensor(g["omega_init"], device=dev),
+                                   int(g["n_poly"]))
+
+
+def make_decoders(vlg, g, K, dev="cuda"):
+    arrs = Hh.decoder_arrays(g)
+    ens = vlg.DecoderEnsemble.from_arrays(*[arrs[k] for k in Hh.DEC_KEYS], dev)
+    return ens[:K]
+
+
+MC_CASES = ["ens_seed12_euclid", "ens_seed12_entropy", "ens_seed12_cov_k3", "synth_np8_T256", "synth_np4_T130"]
+
+
+@pytest.mark.parametrize("tag", MC_CASES)
+def test_fp32_steps_match_reference_goldens(vlg, tag):
+    """Explicit recorded draws, S Adam steps: per-step energy, then omega / m / v."""
+    g = Hh.load(tag)
+    K, T, M, S = int(g["K"]), int(g["T"]), int(g["M"]), int(g["steps"])
+    draws = Hh.regen_draws(g)[:S]
+    model = make_model(vlg, g)
+    dec = make_decoders(vlg, g, K)
+    t = torch.linspace(0, 1, T, device="cuda")
+    e_last, trace = vlg.optimize_splines(model, dec, t, S, M=M, draws=draws, precision="fp32", return_trace=True)
+    trace = trace.cpu().numpy()
+    rel = np.abs(trace / g["energy_f64"] - 1).max()
+    assert rel < FP32_STEP_TOL
+    assert rel < 5e-6, f"fp32 kernel should track the fp64 reference far inside the stated tolerance, got {rel}"
+    assert np.abs(trace / g["energy_f32"] - 1).max() < 5e-6
+    assert np.array_equal(e_last.cpu().numpy(), trace[-1])
+    assert np.abs(model.omega.cpu().numpy() - g["omega_f64"]).max() < 5e-6
+    assert Hh.relerr(model.adam_m.cpu().numpy(), g["m_f64"]) < 2e-5
+    assert Hh.relerr(model.adam_v.cpu().numpy(), g["v_f64"]) < 4e-5
+    assert model.step_count == S
+
+
+def test_fp32_gradient_via_first_adam_moment(vlg):
+    """After one step from zero state m = (1-beta1) * grad: checks d(loss)/d(omega)."""
+    g = Hh.load("ens_seed12_euclid")
+    draws = Hh.regen_draws(g)[:1]
+    model = make_model(vlg, g)
+    dec = make_decoders(vlg, g, 10)
+    t = torch.linspace(0, 1, 2000, device="cuda")
+    vlg.optimize_splines(model, dec, t, 1, M=2, draws=draws, precision="fp32")
+    grad = model.adam_m.cpu().numpy().astype(np.float64) / (1 - 0.9)
+    assert Hh.relerr(grad, g["grad0_f64"]) < 2e-5
+    assert np.abs(model.omega.cpu().numpy() - g["omega1_f64"]).max() < 1e-6
+
+
+def test_forward_energy_and_spline_points(vlg):
+    g = Hh.load("ens_seed12_entropy")
+    draws = Hh.regen_draws(g)[:1]
+    model = make_model(vlg, g)
+    dec = make_decoders(vlg, g, 10)
+    t = torch.linspace(0, 1, 2000, device="cuda")
+    E = vlg.compute_energy_mc(model, dec, t, M=2, draws=draws, precision="fp32").cpu().numpy()
+    assert np.abs(E / g["energy_f64"][0] - 1).max() < 5e-6
+    z = model(t).cpu().numpy()
+    zo = O.spline_points(g["a"], g["b"], g["omega_init"], g["basis"], Hh.tgrid(2000), int(g["n_poly"]))
+    assert np.abs(z - zo).max() < 2e-6
+
+
+def test_counter_draws_match_oracle_stream(vlg):
+    """draws=NULL: the in-kernel Philox stream equals oracle.counter_draws (same energies)."""
+    g = Hh.load("synth_np8_T256")
+    K, T, M = int(g["K"]), int(g["T"]), int(g["M"])
+    N = g["a"].shape[0]
+    model = make_model(vlg, g)
+    dec = make_decoders(vlg, g, K)
+    t = torch.linspace(0, 1, T, device="cuda")
+    seed, id0, S = 0x1234567811, 1000, 3
+    _, trace = vlg.optimize_splines(model, dec, t, S, M=M, seed=seed, curve_id0=id0, precision="fp32", return_trace=True)
+    draws = np.stack([O.counter_draws(seed, np.arange(N) + id0, s, T, M, K) for s in range(S)])
+    decs = Hh.decoder_list(Hh.decoder_arrays(g), K, np.float64)
+    r = O.optimize_steps(g["a"].astype(np.float64), g["b"].astype(np.float64), g["omega_init"].astype(np.float64),
+                         g["basis"].astype(np.float64), Hh.tgrid(T, np.float64), int(g["n_poly"]), decs, draws, S)
+    assert np.abs(trace.cpu().numpy() / r["energy"] - 1).max() < 5e-6
+    assert np.abs(model.omega.cpu().numpy() - r["omega"]).max() < 5e-6
+
+
+def test_results_do_not_depend_on_sharding_or_chunking(vlg):
+    """Curves are independent and draws are keyed on the global curve id: splitting the pair
+    list (multi-GPU sharding) or the step range (chunked launches) is bit-identical."""
+    g = Hh.load("synth_np4_T130")
+    K, T, M = int(g["K"]), int(g["T"]), int(g["M"])
+    N = g["a"].shape[0]
+    dec = make_decoders(vlg, g, K)
+    t = torch.linspace(0, 1, T, device="cuda")
+    full = make_model(vlg, g)
+    e_full = vlg.optimize_splines(full, dec, t, 4, M=M, seed=9, curve_id0=50, precision="fp32")
+    # two shards
+    parts = []
+    for lo, hi in ((0, 2), (2, N)):
+        sub = {k: (v[lo:hi] if k in ("a", "b", "omega_init") else v) for k, v in g.items()}
+        m = make_model(vlg, sub)
+        e = vlg.optimize_splines(m, dec, t, 4, M=M, seed=9, curve_id0=50 + lo, precision="fp32")
+        parts.append((m.omega, e))
+    assert torch.equal(torch.cat([p[0] for p in parts]), full.omega)
+    assert torch.equal(torch.cat([p[1] for p in parts]), e_full)
+    # two step chunks
+    ch = make_model(vlg, g)
+    vlg.optimize_splines(ch, dec, t, 3, M=M, seed=9, curve_id0=50, precision="fp32")
+    e2 = vlg.optimize_splines(ch, dec, t, 1, M=M, seed=9, curve_id0=50, precision="fp32")
+    assert torch.equal(ch.omega, full.omega) and torch.equal(e2, e_full)
+
+
+def test_single_decoder_path(vlg):
+    """BASELINE config 2: deterministic energy, 6 steps, then the poly-line length."""
+    g = Hh.load("single_seed123")
+    model = make_model(vlg, g)
+    dec = make_decoders(vlg, g, 1)
+    t = torch.linspace(0, 1, 2000, device="cuda")
+    E0 = vlg.compute_energy(model, dec, t).cpu().numpy()
+    # sums of tiny differences of large numbers: fp32 noise of the reference itself is ~1e-4 here
+    assert np.abs(E0 / g["energy_f64"][0] - 1).max() < 5e-4
+    S = int(g["steps"])
+    _, trace = vlg.optimize_splines(model, dec, t, S, M=1, precision="fp32", return_trace=True)
+    assert np.abs(trace.cpu().numpy() / g["energy_f64"] - 1).max() < 5e-4
+    L = vlg.compute_geodesic_lengths(model, dec, t).cpu().numpy()
+    assert np.abs(L / g["length_f64"] - 1).max() < 2e-4
+
+
+def test_std_field(vlg):
+    g = Hh.load("std_field_seed12")
+    dec = make_decoders(vlg, Hh.load("evae_seed12_decoders"), 10)
+    s = vlg.ensemble_std_norm(dec, torch.tensor(g["grid"], device="cuda")).cpu().numpy()
+    assert np.abs(s / g["std_norm_f64"] - 1).max() < 2e-5
+    s3 = vlg.ensemble_std_norm(dec[:3], torch.tensor(g["grid"][:77], device="cuda")).cpu().numpy()
+    ref3 = O.ensemble_std_norm(g["grid"][:77].astype(np.float64),
+                               Hh.decoder_list(Hh.load("evae_seed12_decoders"), 3, np.float64))
+    assert np.abs(s3 / ref3 - 1).max() < 2e-5
+
+
+def test_spline_fit(vlg):
+    g = Hh.load("lbfgs_fit")
+    paths = [torch.tensor(g["targets"][i, :L]) for i, L in enumerate(g["lens"])]
+    a, b, om = vlg.fit_splines_to_paths(paths, torch.tensor(g["basis"]), 4, "cuda")
+    for i, L in enumerate(g["lens"]):
+        ref = O.fit_spline_to_path(g["targets"][i, :L], g["basis"], 4)
+        assert np.abs(om[i].cpu().numpy() - ref).max() < 2e-5
+        assert np.abs(om[i].cpu().numpy() - g["omega_lbfgs"][i]).max() < 5e-3
+        assert np.array_equal(a[i].cpu().numpy(), g["targets"][i, 0])
+        assert np.array_equal(b[i].cpu().numpy(), g["targets"][i, L - 1])
+
+
+@pytest.mark.parametrize("T,N,K,M,n_poly", [(2, 1, 1, 1, 1), (3, 2, 2, 2, 2), (128, 3, 3, 4, 4), (129, 2, 5, 1, 8),
+                                           (255, 1, 16, 2, 4)])
+def test_edge_shapes_against_oracle(vlg, T, N, K, M, n_poly):
+    """Ragged / minimal sizes: T=2 (one segment), tile boundaries (128, 129, 255), M up to 4,
+    K up to 16, single curve."""
+    rng = np.random.default_rng(T * 31 + K)
+    torch.manual_seed(T)
+    W = dict(W1=rng.normal(size=(K, 128, 2)) * 0.7, b1=rng.normal(size=(K, 128)) * 0.3,
+             W2=rng.normal(size=(K, 128, 128)) * 0.09, b2=rng.normal(size=(K, 128)) * 0.1,
+             W3=rng.normal(size=(K, 50, 128)) * 0.09, b3=rng.normal(size=(K, 50)) * 0.1)
+    W = {k: v.astype(np.float32) for k, v in W.items()}
+    basis, _ = vlg.construct_nullspace_basis(n_poly)
+    g = dict(a=rng.uniform(-3, 3, (N, 2)).astype(np.float32), b=rng.uniform(-3, 3, (N, 2)).astype(np.float32),
+             omega_init=(0.1 * rng.normal(size=(N, n_poly + 1, 2))).astype(np.float32), basis=basis.numpy(),
+             n_poly=n_poly, **W)
+    S = 2
+    draws = rng.integers(0, K, size=(S, M, 2, T - 1, N))
+    model = make_model(vlg, g)
+    dec = make_decoders(vlg, g, K)
+    t = torch.linspace(0, 1, T, device="cuda")
+    _, trace = vlg.optimize_splines(model, dec, t, S, M=M, draws=draws, precision="fp32", return_trace=True)
+    r = O.optimize_steps(g["a"].astype(np.float64), g["b"].astype(np.float64), g["omega_init"].astype(np.float64),
+                         g["basis"].astype(np.float64), Hh.tgrid(T, np.float64), n_poly,
+                         Hh.decoder_list(W, K, np.float64), draws, S)
+    assert np.abs(trace.cpu().numpy() / r["energy"] - 1).max() < 1e-5
+    assert np.abs(model.omega.cpu().numpy() - r["omega"]).max() < 5e-6
+
+
+def test_full_size_config1_teacher_forced(vlg):
+    """BASELINE config 1 at full size (45 curves, T=2000, K=10, M=2): one step, oracle fp64."""
+    s = Hh.load("splines_seed12_euclidean_10")
+    g = dict(a=s["a"], b=s["b"], omega_init=s["omega_init"], basis=s["basis"], n_poly=int(s["n_poly"]))
+    N, T, K, M = 45, 2000, 10, 2
+    gen = torch.Generator().manual_seed(2024)
+    draws = torch.randint(0, K, (1, M, 2, T - 1, N), generator=gen).numpy()
+    model = make_model(vlg, g)
+    dec = make_decoders(vlg, Hh.load("evae_seed12_decoders"), K)
+    t = torch.linspace(0, 1, T, device="cuda")
+    E = vlg.optimize_splines(model, dec, t, 1, M=M, draws=draws, precision="fp32").cpu().numpy()
+    decs = Hh.decoder_list(Hh.load("evae_seed12_decoders"), K, np.float64)
+    r = O.optimize_steps(g["a"].astype(np.float64), g["b"].astype(np.float64), g["omega_init"].astype(np.float64),
+                         g["basis"].astype(np.float64), Hh.tgrid(T, np.float64), 4, decs, draws, 1)
+    assert np.abs(E / r["energy"][0] - 1).max() < 5e-6
+    assert np.abs(model.omega.cpu().numpy() - r["omega"]).max() < 2e-6
+    # sanity against the reference's committed result: same order of magnitude of sqrt(E)
+    assert 0.3 < np.median(np.sqrt(E) / s["committed_geodesic_length"]) < 3.0
+
+
+def test_errors_are_loud(vlg):
+    g = Hh.load("synth_np4_T130")
+    model = make_model(vlg, g)
+    dec = make_decoders(vlg, g, 4)
+    t = torch.linspace(0, 1, 130, device="cuda")
+    with pytest.raises(vlg.VlgError):
+        vlg.optimize_splines(model, dec, t, 1, M=9, precision="fp32")        # M too large
+    with pytest.raises(vlg.VlgError):
+        vlg.optimize_splines(model, dec, t.cpu(), 1, M=1, precision="fp32")  # CPU tensor
+    with pytest.raises(vlg.VlgError):
+        vlg.optimize_splines(model, dec, t, 1, M=1, draws=np.zeros((1, 1, 2, 5, 5)), precision="fp32")

@@ -1,0 +1,156 @@
+// Shared device helpers and the packed-decoder layout.  sm_100a only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vlg {
+
+constexpr int H = 128;          // hidden width of the decoder MLP (src/train.py:80-85)
+constexpr int XP = 64;          // padded output width (X <= 64; tasic-pca50: X = 50)
+constexpr int TILE_ROWS = 128;  // curve points per tile (= MMA M, = TMEM lanes)
+constexpr int TILE_SEGS = 127;  // curve segments per tile: adjacent tiles share one point
+constexpr int MAX_NPOLY = 8;
+constexpr int MAX_KB = MAX_NPOLY + 1;
+constexpr int MAX_M = 4;
+constexpr int MAX_K = 255;      // decoder index travels as uint8; 255 = "none"
+
+// ---------------------------------------------------------------------------------------
+// Packed decoder image (device memory), produced by vlg_pack_decoders.
+//   header (256 B) followed by K per-decoder records of DEC_FLOATS floats.
+// Per decoder (float offsets):
+//   SMALL   : W1[128][2] | b1[128] | b2[128] | b3[64]                      (576 floats)
+//   W2T     : [in 128][out 128]    fp32, B operand of the SIMT forward GEMM
+//   W2      : [out 128][in 128]    fp32, B operand of the SIMT backward GEMM
+//   W3T     : [in 128][out 64]     fp32 (cols >= X are zero)
+//   W3      : [out 64][in 128]     fp32 (rows >= X are zero)
+//   W2_UMMA : tcgen05 canonical no-swizzle image [k/4][n 128][k%4]: K-major B for
+//             h1*W2^T (SBO=128 B, LBO=2048 B) and, read MN-major, B for dh2*W2
+//   W3_UMMA : same for W3: [k/4][n 64][k%4]
+//   W2_LO / W3_LO : residual (w - tf32(w)) images for the 3xTF32 variant
+// ---------------------------------------------------------------------------------------
+struct PackedHeader {
+  uint32_t magic;    // 'VLG1'
+  int32_t K, Hdim, X;
+  uint32_t dec_floats;
+  uint32_t pad[59];
+};
+static_assert(sizeof(PackedHeader) == 256, "header must be 256 bytes");
+constexpr uint32_t PACK_MAGIC = 0x31474c56u;
+
+constexpr int OFF_W1 = 0;
+constexpr int OFF_B1 = 256;
+constexpr int OFF_B2 = 384;
+constexpr int OFF_B3 = 512;
+constexpr int OFF_W2T = 576;
+constexpr int OFF_W2 = OFF_W2T + H * H;
+constexpr int OFF_W3T = OFF_W2 + H * H;
+constexpr int OFF_W3 = OFF_W3T + H * XP;
+constexpr int OFF_W2_UMMA = OFF_W3 + XP * H;
+constexpr int OFF_W3_UMMA = OFF_W2_UMMA + H * H;
+constexpr int OFF_W2_LO = OFF_W3_UMMA + XP * H;
+constexpr int OFF_W3_LO = OFF_W2_LO + H * H;
+constexpr int DEC_FLOATS = OFF_W3_LO + XP * H;  // 576 + 4*16384 + 4*8192 + ... floats
+
+__host__ __device__ inline const float* dec_ptr(const void* packed, int k) {
+  return reinterpret_cast<const float*>(reinterpret_cast<const char*>(packed) + sizeof(PackedHeader)) +
+         size_t(k) * DEC_FLOATS;
+}
+
+// ---------------------------------------------------------------------------------------
+// Philox4x32-10: counter-based decoder draws.  Same definition as
+// oracle/geodesic_oracle.py:counter_draws (counter = (segment, step, curve id, m/2),
+// key = seed; word w -> decoder index (w*K)>>32).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+    uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += W0;
+    k.y += W1;
+  }
+  return c;
+}
+
+// Decoder index for (curve, step, MC sample m, role, segment).
+__device__ __forceinline__ void counter_draws4(uint64_t seed, uint32_t curve, uint32_t step,
+                                               uint32_t seg, uint32_t mpair, uint32_t K,
+                                               uint32_t out[4]) {
+  uint4 w = philox4x32_10(make_uint4(seg, step, curve, mpair),
+                          make_uint2(uint32_t(seed), uint32_t(seed >> 32)));
+  out[0] = __umulhi(w.x, K);
+  out[1] = __umulhi(w.y, K);
+  out[2] = __umulhi(w.z, K);
+  out[3] = __umulhi(w.w, K);
+}
+
+// ---------------------------------------------------------------------------------------
+// Spline helpers (src/optimize.py:22-35).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void seg_coords(float t, int n_poly, int& seg, float& u) {
+  float tn = t * float(n_poly);
+  int s = int(floorf(tn));
+  seg = s < n_poly - 1 ? s : n_poly - 1;
+  u = tn - float(seg);
+}
+
+// z = (1-t) a + t b + sum_i u^i coef[seg][i]   (coef = basis @ omega, [n_poly][4][2])
+__device__ __forceinline__ float2 spline_point(float t, int n_poly, const float* coef, float2 a,
+                                               float2 b) {
+  int seg;
+  float u;
+  seg_coords(t, n_poly, seg, u);
+  const float* c = coef + seg * 8;
+  float u2 = u * u, u3 = u2 * u;
+  float px = c[0] + u * c[2] + u2 * c[4] + u3 * c[6];
+  float py = c[1] + u * c[3] + u2 * c[5] + u3 * c[7];
+  float omt = 1.0f - t;
+  return make_float2(omt * a.x + t * b.x + px, omt * a.y + t * b.y + py);
+}
+
+// Row of the design matrix P[t][k] = sum_i u^i basis[4 seg + i][k].
+__device__ __forceinline__ void design_row(float t, int n_poly, int Kb, const float* basis, float* P) {
+  int seg;
+  float u;
+  seg_coords(t, n_poly, seg, u);
+  float u2 = u * u, u3 = u2 * u;
+  const float* r = basis + seg * 4 * Kb;
+#pragma unroll
+  for (int k = 0; k < MAX_KB; ++k)
+    if (k < Kb) P[k] = r[k] + u * r[Kb + k] + u2 * r[2 * Kb + k] + u3 * r[3 * Kb + k];
+}
+
+// Adam scalars for 1-based step s, as torch computes them in double (torch/optim/adam.py):
+// step_size = lr / (1 - beta1^s), denom = sqrt(v) / sqrt(1 - beta2^s) + eps.
+struct AdamScalars {
+  float step_size, bc2_sqrt;
+};
+__device__ inline AdamScalars adam_scalars(int step, double lr, double beta1, double beta2) {
+  double bc1 = 1.0 - pow(beta1, double(step));
+  double bc2 = 1.0 - pow(beta2, double(step));
+  AdamScalars s;
+  s.step_size = float(lr / bc1);
+  s.bc2_sqrt = float(sqrt(bc2));
+  return s;
+}
+
+// one_minus_b1 = float(1 - beta1), beta2f = float(beta2), one_minus_b2 = float(1 - beta2):
+// rounded from the double expressions exactly as torch hands them to lerp_/mul_/addcmul_.
+__device__ __forceinline__ void adam_update(float& p, float& m, float& v, float g, AdamScalars s,
+                                            float one_minus_b1, float beta2f, float one_minus_b2,
+                                            float eps) {
+  m = m + (g - m) * one_minus_b1;
+  v = v * beta2f + (one_minus_b2 * g) * g;
+  float denom = sqrtf(v) / s.bc2_sqrt + eps;
+  p = p - s.step_size * (m / denom);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace vlg
