@@ -227,3 +227,65 @@ def test_errors_are_loud(vlg):
         vlg.optimize_splines(model, dec, t.cpu(), 1, M=1, precision="fp32")  # CPU tensor
     with pytest.raises(vlg.VlgError):
         vlg.optimize_splines(model, dec, t, 1, M=1, draws=np.zeros((1, 1, 2, 5, 5)), precision="fp32")
+
+
+# ---------------------------------------------------------------------------------------------
+# tensor-core (tcgen05 kind::tf32) variant.  north_star tolerance: <= 1e-3 relative on geodesic
+# lengths (sqrt(E)), i.e. <= 2e-3 on energies.
+# ---------------------------------------------------------------------------------------------
+TF32_LENGTH_TOL = 1e-3
+
+
+@pytest.mark.parametrize("tag", ["ens_seed12_euclid", "ens_seed12_entropy", "ens_seed12_cov_k3", "synth_np8_T256",
+                                 "synth_np4_T130"])
+def test_tf32_steps_track_reference(vlg, tag):
+    g = Hh.load(tag)
+    K, T, M, S = int(g["K"]), int(g["T"]), int(g["M"]), int(g["steps"])
+    if M > 2:
+        pytest.skip("tensor-core path is built for M <= 2 (shared-memory budget)")
+    draws = Hh.regen_draws(g)[:S]
+    model = make_model(vlg, g)
+    dec = make_decoders(vlg, g, K)
+    t = torch.linspace(0, 1, T, device="cuda")
+    e_last, trace = vlg.optimize_splines(model, dec, t, S, M=M, draws=draws, precision="tf32", return_trace=True)
+    trace = trace.cpu().numpy()
+    len_rel = np.abs(np.sqrt(trace / g["energy_f64"]) - 1).max()
+    assert len_rel < TF32_LENGTH_TOL, len_rel
+    # gradient quality: first Adam moment after S steps stays close to the fp64 one
+    assert Hh.relerr(model.adam_m.cpu().numpy(), g["m_f64"]) < 3e-2
+    # Adam normalises the gradient, so near-zero gradient components turn tiny errors into
+    # +-lr-sized steps: after S steps omega may differ by a fraction of S*lr = S*1e-3
+    assert np.abs(model.omega.cpu().numpy() - g["omega_f64"]).max() < 0.25 * S * 1e-3
+    print(f"{tag}: tf32 max rel length err {len_rel:.2e}")
+
+
+def test_tf32_forward_energy_full_size(vlg):
+    s = Hh.load("splines_seed12_entropy_10")
+    g = dict(a=s["a"], b=s["b"], omega_init=s["omega_init"], basis=s["basis"], n_poly=int(s["n_poly"]))
+    N, T, K, M = 45, 2000, 10, 2
+    model = make_model(vlg, g)
+    dec = make_decoders(vlg, Hh.load("evae_seed12_decoders"), K)
+    t = torch.linspace(0, 1, T, device="cuda")
+    e32 = vlg.compute_energy_mc(model, dec, t, M=M, seed=3, step=7, precision="fp32").cpu().numpy()
+    etc = vlg.compute_energy_mc(model, dec, t, M=M, seed=3, step=7, precision="tf32").cpu().numpy()
+    assert np.abs(np.sqrt(etc / e32) - 1).max() < TF32_LENGTH_TOL
+
+
+@pytest.mark.parametrize("prec,tol", [("fp32", 2e-5), ("tf32", TF32_LENGTH_TOL)])
+def test_final_length_after_150_steps(vlg, prec, tol):
+    """Long horizon (free-running, not teacher-forced): final sqrt(E) against the reference's own
+    fp64 run with the same recorded draws.  The reference's fp32-vs-fp64 gap is printed beside it."""
+    g = Hh.load("ens_seed12_long")
+    S = int(g["long_steps"])
+    draws = Hh.regen_draws(g)[:S]
+    model = make_model(vlg, g)
+    dec = make_decoders(vlg, Hh.load("evae_seed12_decoders"), 10)
+    t = torch.linspace(0, 1, 2000, device="cuda")
+    _, trace = vlg.optimize_splines(model, dec, t, S, M=2, draws=draws, precision=prec, return_trace=True)
+    trace = trace.cpu().numpy()
+    ref = g["long_energy_f64"]
+    gap_ref32 = np.abs(np.sqrt(g["long_energy_f32"][-1] / ref[-1]) - 1).max()
+    ours = np.abs(np.sqrt(trace[-1] / ref[-1]) - 1).max()
+    print(f"final-length rel err after {S} steps: {prec} kernel {ours:.2e}; reference fp32 vs fp64 {gap_ref32:.2e}")
+    assert ours < tol
+    assert np.abs(np.sqrt(trace / ref) - 1).max() < tol * 2

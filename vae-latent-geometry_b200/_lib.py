@@ -36,6 +36,12 @@ SIGNATURES = {
 }
 
 
+# test hooks declared in include/vlg_selftest.h
+SELFTEST_SIGNATURES = {
+    "vlg_selftest_umma": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+}
+
+
 class VlgError(RuntimeError):
     pass
 
@@ -50,7 +56,7 @@ def load():
             f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
             "vlg_b200 has no CPU / PyTorch fallback.")
     lib = ctypes.CDLL(str(LIB_PATH))
-    for name, (res, args) in SIGNATURES.items():
+    for name, (res, args) in {**SIGNATURES, **SELFTEST_SIGNATURES}.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args

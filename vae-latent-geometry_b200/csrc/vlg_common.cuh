@@ -23,10 +23,13 @@ constexpr int MAX_K = 255;      // decoder index travels as uint8; 255 = "none"
 //   W2      : [out 128][in 128]    fp32, B operand of the SIMT backward GEMM
 //   W3T     : [in 128][out 64]     fp32 (cols >= X are zero)
 //   W3      : [out 64][in 128]     fp32 (rows >= X are zero)
-//   W2_UMMA : tcgen05 canonical no-swizzle image [k/4][n 128][k%4]: K-major B for
-//             h1*W2^T (SBO=128 B, LBO=2048 B) and, read MN-major, B for dh2*W2
-//   W3_UMMA : same for W3: [k/4][n 64][k%4]
-//   W2_LO / W3_LO : residual (w - tf32(w)) images for the 3xTF32 variant
+//   tcgen05 B-operand images, canonical no-swizzle K-major layout img[k/4][n][k%4]
+//   (8x16B core matrices; SBO = 128 B between 8-row groups, LBO = N*16 B between k-chunks),
+//   values pre-rounded to TF32 (round-to-nearest); the *_LO images hold w - tf32(w):
+//   W2_UMMA  : B[n=out][k=in]  = W2[out][in]   N=128 K=128   (h1 * W2^T)
+//   W3_UMMA  : B[n=out][k=in]  = W3[out][in]   N=64  K=128   (h2 * W3^T, rows >= X zero)
+//   W3T_UMMA : B[n=in][k=out]  = W3[out][in]   N=128 K=64    (dx  * W3)
+//   W2T_UMMA : B[n=in][k=out]  = W2[out][in]   N=128 K=128   (dh2 * W2)
 // ---------------------------------------------------------------------------------------
 struct PackedHeader {
   uint32_t magic;    // 'VLG1'
@@ -47,9 +50,14 @@ constexpr int OFF_W3T = OFF_W2 + H * H;
 constexpr int OFF_W3 = OFF_W3T + H * XP;
 constexpr int OFF_W2_UMMA = OFF_W3 + XP * H;
 constexpr int OFF_W3_UMMA = OFF_W2_UMMA + H * H;
-constexpr int OFF_W2_LO = OFF_W3_UMMA + XP * H;
+constexpr int OFF_W3T_UMMA = OFF_W3_UMMA + XP * H;
+constexpr int OFF_W2T_UMMA = OFF_W3T_UMMA + XP * H;
+constexpr int OFF_W2_LO = OFF_W2T_UMMA + H * H;
 constexpr int OFF_W3_LO = OFF_W2_LO + H * H;
-constexpr int DEC_FLOATS = OFF_W3_LO + XP * H;  // 576 + 4*16384 + 4*8192 + ... floats
+constexpr int OFF_W3T_LO = OFF_W3_LO + XP * H;
+constexpr int OFF_W2T_LO = OFF_W3T_LO + XP * H;
+constexpr int DEC_FLOATS = OFF_W2T_LO + H * H;
+static_assert(DEC_FLOATS % 64 == 0 && OFF_W2_UMMA % 4 == 0, "images must stay 16-byte aligned");
 
 __host__ __device__ inline const float* dec_ptr(const void* packed, int k) {
   return reinterpret_cast<const float*>(reinterpret_cast<const char*>(packed) + sizeof(PackedHeader)) +

@@ -43,20 +43,26 @@ __global__ void pack_kernel(const float* __restrict__ W1, const float* __restric
     const float w = w2[i];
     d[OFF_W2 + i] = w;
     d[OFF_W2T + in * H + o] = w;
-    const int u = ((in >> 2) * H + o) * 4 + (in & 3);
+    const int u = ((in >> 2) * H + o) * 4 + (in & 3);   // B[n=o][k=in]
+    const int ut = ((o >> 2) * H + in) * 4 + (o & 3);   // B[n=in][k=o]
     const float hi = tf32_rn(w);
     d[OFF_W2_UMMA + u] = hi;
     d[OFF_W2_LO + u] = w - hi;
+    d[OFF_W2T_UMMA + ut] = hi;
+    d[OFF_W2T_LO + ut] = w - hi;
   }
   for (int i = threadIdx.x; i < XP * H; i += blockDim.x) {
     const int o = i / H, in = i % H;  // W3[o][in], zero rows o >= X
     const float w = o < X ? w3[o * H + in] : 0.f;
     d[OFF_W3 + i] = w;
     d[OFF_W3T + in * XP + o] = w;
-    const int u = ((in >> 2) * XP + o) * 4 + (in & 3);
+    const int u = ((in >> 2) * XP + o) * 4 + (in & 3);   // B[n=o][k=in], N = 64
+    const int ut = ((o >> 2) * H + in) * 4 + (o & 3);    // B[n=in][k=o], N = 128, K = 64
     const float hi = tf32_rn(w);
     d[OFF_W3_UMMA + u] = hi;
     d[OFF_W3_LO + u] = w - hi;
+    d[OFF_W3T_UMMA + ut] = hi;
+    d[OFF_W3T_LO + ut] = w - hi;
   }
 }
 

@@ -1,0 +1,124 @@
+// Unit-test kernel for the tcgen05 building blocks (see include/vlg_selftest.h).
+#include "../../include/vlg.h"
+#include "../../include/vlg_selftest.h"
+#include "vlg_common.cuh"
+#include "vlg_tcgen05.cuh"
+
+namespace vlg {
+namespace {
+
+using namespace tc;
+
+// one CTA, 128 threads.  Rows of A / D = TMEM lanes.
+__global__ void __launch_bounds__(128) umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ Bimg,
+                                                            const float* __restrict__ Blo, float* __restrict__ D,
+                                                            int N, int K, int mn_major, int split3, int lbo_o, int sbo_o, int kstep_o) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  float* sB = reinterpret_cast<float*>(smem);              // N*K floats
+  float* sBlo = sB + N * K;                                // N*K floats (split3)
+  __shared__ __align__(8) uint64_t bar_b, bar_mma;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  // contraction length / output width of this run
+  const int KK = mn_major ? N : K;   // A has KK columns
+  const int NN = mn_major ? K : N;   // D has NN columns
+
+  if (tid == 0) {
+    mbar_init(&bar_b, 1);
+    mbar_init(&bar_mma, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t lane_base = uint32_t(warp * 32) << 16;
+  const uint32_t colA = 0, colAlo = 128, colD = 256;
+
+  if (tid == 0) {
+    const uint32_t bytes = uint32_t(N) * K * 4;
+    mbar_expect_tx(&bar_b, split3 ? 2 * bytes : bytes);
+    bulk_g2s(sB, Bimg, bytes, &bar_b);
+    if (split3) bulk_g2s(sBlo, Blo, bytes, &bar_b);
+  }
+  // A row -> TMEM (hi and, for split3, the residual)
+  for (int c0 = 0; c0 < KK; c0 += 16) {
+    uint32_t v[16], lo[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float a = A[size_t(tid) * KK + c0 + j];
+      if (split3) {
+        const uint32_t hi = __float_as_uint(a) & 0xFFFFE000u;
+        v[j] = hi;
+        lo[j] = __float_as_uint(a - __uint_as_float(hi));
+      } else {
+        v[j] = __float_as_uint(a);
+      }
+    }
+    tmem_st16(tmem + lane_base + colA + c0, v);
+    if (split3) tmem_st16(tmem + lane_base + colAlo + c0, lo);
+  }
+  tmem_wait_st();
+  tc_fence_before();
+  __syncthreads();
+
+  if (tid == 0) {
+    tc_fence_after();
+    mbar_wait(&bar_b, 0);
+    const uint32_t idesc = umma_idesc_tf32(NN, mn_major);
+    const int nk = KK / 8;
+    for (int pass = 0; pass < (split3 ? 3 : 1); ++pass) {
+      // pass 0: Ahi*Bhi, pass 1: Alo*Bhi, pass 2: Ahi*Blo
+      const uint32_t a_col = (pass == 1) ? colAlo : colA;
+      const float* b_src = (pass == 2) ? sBlo : sB;
+      for (int ks = 0; ks < nk; ++ks) {
+        uint64_t desc;
+        if (!mn_major) {
+          // K-major: two 16B k-chunks per MMA, LBO = N*16 (next k-chunk), SBO = 128 (next 8 rows)
+          desc = umma_smem_desc(smem_u32(b_src) + uint32_t(ks) * 2u * uint32_t(N) * 16u, uint32_t(N) * 16u, 128u);
+        } else {
+          // MN-major: k (=image row n) advances by 16 B; 8 k per MMA = 128 B; MN groups of 4 at SBO = N*16
+          desc = umma_smem_desc(smem_u32(b_src) + uint32_t(ks) * (kstep_o ? uint32_t(kstep_o) : 128u), lbo_o ? uint32_t(lbo_o) : 128u,
+                                sbo_o ? uint32_t(sbo_o) : uint32_t(N) * 16u);
+        }
+        umma_tf32_ts(tmem + colD, tmem + a_col + uint32_t(ks) * 8u, desc, idesc, (pass | ks) ? 1u : 0u);
+      }
+    }
+    umma_commit(&bar_mma);
+  }
+  mbar_wait(&bar_mma, 0);
+  tc_fence_after();
+  for (int c0 = 0; c0 < NN; c0 += 16) {
+    uint32_t v[16];
+    tmem_ld16(tmem + lane_base + colD + c0, v);
+    tmem_wait_ld();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) D[size_t(tid) * NN + c0 + j] = __uint_as_float(v[j]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace
+}  // namespace vlg
+
+extern "C" int vlg_selftest_umma_ex(const float* A, const float* Bimg, const float* Blo, float* D, int N, int K,
+                                    int b_mn_major, int split3, int lbo, int sbo, int kstep, void* stream);
+
+extern "C" int vlg_selftest_umma(const float* A, const float* Bimg, const float* Blo, float* D, int N, int K,
+                                 int b_mn_major, int split3, void* stream) {
+  return vlg_selftest_umma_ex(A, Bimg, Blo, D, N, K, b_mn_major, split3, 0, 0, 0, stream);
+}
+
+extern "C" int vlg_selftest_umma_ex(const float* A, const float* Bimg, const float* Blo, float* D, int N, int K,
+                                    int b_mn_major, int split3, int lbo, int sbo, int kstep, void* stream) {
+  if (!A || !Bimg || !D || (split3 && !Blo)) return VLG_ERR_INVALID_ARGUMENT;
+  if (N % 16 || K % 16 || N < 16 || N > 128 || K < 16 || K > 128) return VLG_ERR_UNSUPPORTED;
+  const size_t smem = size_t(N) * K * 4 * 2;
+  cudaError_t e = cudaFuncSetAttribute(vlg::umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  if (e != cudaSuccess) return VLG_ERR_CUDA;
+  vlg::umma_selftest_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(A, Bimg, Blo, D, N, K, b_mn_major, split3, lbo, sbo, kstep);
+  return cudaGetLastError() == cudaSuccess ? VLG_OK : VLG_ERR_CUDA;
+}
