@@ -9,7 +9,9 @@ import ctypes
 from ctypes import c_char_p, c_double, c_int, c_int64, c_size_t, c_uint64, c_void_p
 from pathlib import Path
 
-LIB_PATH = Path(__file__).resolve().parent / "libvlg_b200.so"
+import os
+
+LIB_PATH = Path(os.environ.get("VLG_B200_LIB", Path(__file__).resolve().parent / "libvlg_b200.so"))
 
 _lib = None
 

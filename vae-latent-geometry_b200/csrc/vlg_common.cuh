@@ -18,7 +18,7 @@ constexpr int MAX_K = 255;      // decoder index travels as uint8; 255 = "none"
 // Packed decoder image (device memory), produced by vlg_pack_decoders.
 //   header (256 B) followed by K per-decoder records of DEC_FLOATS floats.
 // Per decoder (float offsets):
-//   SMALL   : W1[128][2] | b1[128] | b2[128] | b3[64]                      (576 floats)
+//   SMALL   : W1[:,0][128] | W1[:,1][128] | b1[128] | b2[128] | b3[64]    (576 floats)
 //   W2T     : [in 128][out 128]    fp32, B operand of the SIMT forward GEMM
 //   W2      : [out 128][in 128]    fp32, B operand of the SIMT backward GEMM
 //   W3T     : [in 128][out 64]     fp32 (cols >= X are zero)
@@ -40,7 +40,8 @@ struct PackedHeader {
 static_assert(sizeof(PackedHeader) == 256, "header must be 256 bytes");
 constexpr uint32_t PACK_MAGIC = 0x31474c56u;
 
-constexpr int OFF_W1 = 0;
+constexpr int OFF_W1X = 0;    // W1[c][0], c < 128
+constexpr int OFF_W1Y = 128;  // W1[c][1]
 constexpr int OFF_B1 = 256;
 constexpr int OFF_B2 = 384;
 constexpr int OFF_B3 = 512;

@@ -32,7 +32,7 @@ __global__ void pack_kernel(const float* __restrict__ W1, const float* __restric
   const float* w1 = W1 + size_t(k) * H * 2;
   const float* w2 = W2 + size_t(k) * H * H;
   const float* w3 = W3 + size_t(k) * X * H;
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) d[OFF_W1 + i] = w1[i];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) d[((i & 1) ? OFF_W1Y : OFF_W1X) + (i >> 1)] = w1[i];
   for (int i = threadIdx.x; i < H; i += blockDim.x) {
     d[OFF_B1 + i] = b1[size_t(k) * H + i];
     d[OFF_B2 + i] = b2[size_t(k) * H + i];
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(128) std_norm_kernel(const void* packed, int K
   for (int k = 0; k < K; ++k) {
     const float* d = dec_ptr(packed, k);
     {
-      const float wa = d[OFF_W1 + 2 * j], wb = d[OFF_W1 + 2 * j + 1], bb = d[OFF_B1 + j];
+      const float wa = d[OFF_W1X + j], wb = d[OFF_W1Y + j], bb = d[OFF_B1 + j];
 #pragma unroll
       for (int p = 0; p < SP; ++p) h1[p][j] = fmaxf(fmaf(wb, zz[p][1], fmaf(wa, zz[p][0], bb)), 0.f);
     }

@@ -93,7 +93,7 @@ __device__ __forceinline__ void store_tile_T(float* As, const float (&acc)[8][8]
 __device__ __forceinline__ float pre1(const float* sw, int c, float2 z) {
   // first-layer pre-activation; the same expression is used in forward and backward so
   // the recomputed ReLU mask is bit-identical.
-  return fmaf(sw[OFF_W1 + 2 * c + 1], z.y, fmaf(sw[OFF_W1 + 2 * c], z.x, sw[OFF_B1 + c]));
+  return fmaf(sw[OFF_W1Y + c], z.y, fmaf(sw[OFF_W1X + c], z.x, sw[OFF_B1 + c]));
 }
 
 struct Smem {
@@ -373,8 +373,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) simt_curve_kernel(StepParams p) {
             for (int j = 0; j < 8; ++j) {
               const int c = col8(tx, j);
               if (pre1(s.sw, c, z) > 0.f) {
-                dx = fmaf(acc[i][j], s.sw[OFF_W1 + 2 * c], dx);
-                dy = fmaf(acc[i][j], s.sw[OFF_W1 + 2 * c + 1], dy);
+                dx = fmaf(acc[i][j], s.sw[OFF_W1X + c], dx);
+                dy = fmaf(acc[i][j], s.sw[OFF_W1Y + c], dy);
               }
             }
 #pragma unroll

@@ -1,16 +1,18 @@
 // tcgen05 (TF32) geodesic step kernel -- the tensor-core variant (<=1e-3 relative on lengths).
 //
-// One CTA (320 threads) = one curve, persistent over `steps` Adam steps.  The two 128-wide
+// One CTA (576 threads) = one curve, persistent over `steps` Adam steps.  The two 128-wide
 // decoder layers and their transposes run as tcgen05.mma kind::tf32 with
-//   * M = 128 curve points = the 128 TMEM lanes (one thread owns one point / one lane),
+//   * M = 128 curve points = the 128 TMEM lanes,
 //   * the A operand (activations) living in TENSOR MEMORY: the epilogue threads write the
 //     next layer's input back with tcgen05.st, in place of the accumulator they just read,
 //   * the B operand (weights) streamed from L2 into a shared-memory ring by the TMA engine
 //     (1-D bulk copies of pre-packed no-swizzle K-major images, mbarrier complete_tx),
 //   * fp32 accumulators in TMEM, read back with tcgen05.ld.
-// Warp roles: warp 0 = weight producer, warp 1 = MMA issuer (one lane), warps 2-5 and 6-9 =
-// two epilogue warpgroups.  Each warpgroup owns a "chain" of 256 TMEM columns and alternate
-// decoders, so that one chain's CUDA-core epilogue overlaps the other chain's MMAs.
+// Warp roles: warp 0 = weight producer, warp 1 = MMA issuer (one lane), warps 2-9 and 10-17 =
+// two epilogue groups of 8 warps.  Each group owns a "chain" of 256 TMEM columns and alternate
+// decoders, so one chain's CUDA-core epilogue overlaps the other chain's MMAs; inside a group
+// two threads share a curve point (TMEM lane) and split its columns, which gives the SM four
+// epilogue warps per scheduler to hide TMEM / shared-memory latency.
 //
 // Per 128-point tile: forward of all K decoders (layer 1 on CUDA cores, exact fp32) ->
 // selected outputs accumulate into Diff[m][segment] (shared memory, fp32) -> energy ->
@@ -26,7 +28,9 @@ namespace {
 
 using namespace tc;
 
-constexpr int TC_THREADS = 320;
+constexpr int TC_THREADS = 576;       // 2 + 16 warps
+constexpr int GROUP_THREADS = 256;    // one epilogue group (chain)
+constexpr int EPI_THREADS = 512;
 constexpr int STAGE_BYTES = 16384;
 constexpr int NSTAGES = 6;
 constexpr int DIFF_STRIDE = 52;
@@ -49,30 +53,42 @@ __device__ __forceinline__ OpInfo op_info(int op) {
   }
 }
 
-__device__ __forceinline__ uint32_t to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
+// round-to-nearest to TF32 for finite values: the tensor core ignores the 13 low mantissa bits
+__device__ __forceinline__ uint32_t tf32_round_bits(uint32_t b) { return b + 0x1000u; }
+// relu, then TF32 round-to-nearest on the bit pattern.  (An integer-max formulation,
+// max(int(bits + 0x1000), 0), produced wrong results when combined with the packed f32x2
+// intrinsics under nvcc 12.9 -- keep the float max.)
+__device__ __forceinline__ uint32_t relu_tf32(float v) { return __float_as_uint(fmaxf(v, 0.f)) + 0x1000u; }
+#ifdef VLG_NO_PACKED
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+#else
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+#endif
 
 __device__ __forceinline__ void named_bar(int id, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 struct TcSmem {
   unsigned char* ring;  // NSTAGES * 16 KB
   float* Diff;          // M*128*52
   uint32_t* mask2;      // K*128*4 words
   uint8_t* sel;         // MAX_M*2*128
-  float* sw;            // 2 * 576
+  float* sw;            // [chain][buf] 576 floats
   float2* zs;           // 128
   float* ts;            // 128
-  float2* dzs;          // 2*128
+  float2* dzs;          // 4*128
   float* coef;          // 64
   float* basis;         // 288
   float* om;            // 56
   float* gacc;          // 20
-  float* red;           // 4*20 + 16
+  float* red;           // 4*20 + 32
   uint64_t* bars;       // full[NSTAGES], empty[NSTAGES], a_ready[2], acc_ready[2]
   uint32_t* tmem_base;
   volatile int* turn;
@@ -83,15 +99,15 @@ __device__ __forceinline__ TcSmem tc_carve(unsigned char* base, int M, int K) {
   s.ring = base;
   float* f = reinterpret_cast<float*>(base + NSTAGES * STAGE_BYTES);
   s.Diff = f; f += M * 128 * DIFF_STRIDE;
-  s.sw = f; f += 2 * 576;
+  s.sw = f; f += 4 * 576;
   s.zs = reinterpret_cast<float2*>(f); f += 256;
   s.ts = f; f += 128;
-  s.dzs = reinterpret_cast<float2*>(f); f += 512;
+  s.dzs = reinterpret_cast<float2*>(f); f += 1024;
   s.coef = f; f += 64;
   s.basis = f; f += 4 * MAX_NPOLY * MAX_KB;
   s.om = f; f += 3 * 2 * MAX_KB + 2;
   s.gacc = f; f += 2 * MAX_KB + 2;
-  s.red = f; f += 96;
+  s.red = f; f += 112;
   s.bars = reinterpret_cast<uint64_t*>(f); f += 2 * (2 * NSTAGES + 4);
   s.tmem_base = reinterpret_cast<uint32_t*>(f); f += 2;
   s.turn = reinterpret_cast<volatile int*>(f); f += 2;
@@ -104,8 +120,8 @@ __device__ __forceinline__ TcSmem tc_carve(unsigned char* base, int M, int K) {
 }  // namespace
 
 static size_t tc_smem_bytes(int M, int K) {
-  size_t fl = size_t(M) * 128 * DIFF_STRIDE + 2 * 576 + 256 + 128 + 512 + 64 + 4 * MAX_NPOLY * MAX_KB +
-              (3 * 2 * MAX_KB + 2) + (2 * MAX_KB + 2) + 96 + 2 * (2 * NSTAGES + 4) + 2 + 2 + MAX_M * 2 * 128 / 4;
+  size_t fl = size_t(M) * 128 * DIFF_STRIDE + 4 * 576 + 256 + 128 + 1024 + 64 + 4 * MAX_NPOLY * MAX_KB +
+              (3 * 2 * MAX_KB + 2) + (2 * MAX_KB + 2) + 112 + 2 * (2 * NSTAGES + 4) + 2 + 2 + MAX_M * 2 * 128 / 4;
   return size_t(NSTAGES) * STAGE_BYTES + fl * 4 + size_t(K) * 128 * 16;
 }
 
@@ -114,7 +130,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n = blockIdx.x;
-  const int M = p.M, K = p.K, T = p.T, n_poly = p.n_poly, Kb = p.Kb, X = p.X;
+  const int M = p.M, K = p.K, T = p.T, n_poly = p.n_poly, Kb = p.Kb;
   TcSmem s = tc_carve(smem_raw, M, K);
   uint64_t* full = s.bars;
   uint64_t* empty = s.bars + NSTAGES;
@@ -127,8 +143,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
     }
-    mbar_init(&a_ready[0], 128);
-    mbar_init(&a_ready[1], 128);
+    mbar_init(&a_ready[0], GROUP_THREADS);
+    mbar_init(&a_ready[1], GROUP_THREADS);
     mbar_init(&acc_ready[0], 1);
     mbar_init(&acc_ready[1], 1);
     *s.turn = 0;
@@ -143,7 +159,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p) {
   // The sequence of tensor-core ops is identical for every tile: for each decoder pair
   // (kA = 2p on chain 0, kB = 2p+1 on chain 1): forward F2(kA) F2(kB) F3(kA) F3(kB), and after
   // all pairs the backward B3(kA) B3(kB) B2(kA) B2(kB).  Producer and MMA issuer walk it in
-  // lock step through the ring; the epilogue warpgroups follow through a_ready / acc_ready.
+  // lock step through the ring; the epilogue groups follow through a_ready / acc_ready.
   const int npairs = (K + 1) / 2;
   const long total_tiles = long(p.steps) * ntiles;
 
@@ -206,50 +222,61 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p) {
               }
     }
   } else {
-    // ================= epilogue warpgroups =================
-    const int wg = (warp - 2) >> 2;             // chain
+    // ================= epilogue groups =================
+    const int ew = warp - 2;                    // 0..15
+    const int chain_id = ew >> 3;               // group / chain
+    const int half = (ew >> 2) & 1;             // which 64 of the 128 columns
     const int row = (warp & 3) * 32 + lane;     // TMEM lane = curve point of the tile
-    const int t256 = wg * 128 + row;            // 0..255 over both warpgroups
+    const int tg = half * 128 + row;            // 0..255 inside the group
+    const int t512 = chain_id * 256 + tg;       // 0..511 over both groups
     const uint32_t lane_addr = uint32_t((warp & 3) * 32) << 16;
-    const uint32_t chain = tmem + lane_addr + uint32_t(wg) * 256u;
+    const uint32_t chain = tmem + lane_addr + uint32_t(chain_id) * 256u;
     const uint32_t colX = chain, colY = chain + 128u;
-    float* sw = s.sw + wg * 576;
+    const int col0 = half * 64;                 // this thread's hidden units
+    const int xc0 = half * 32;                  // this thread's output / G columns
+    const int bar_id = 1 + chain_id;
+    float* swbuf = s.sw + chain_id * 2 * 576;
+    int swsel = 0;
     uint32_t ph_acc = 0;
     const float coefm = 2.0f / float(M);
 
-    for (int i = t256; i < 4 * n_poly * Kb; i += 256) s.basis[i] = p.basis[i];
-    if (t256 < 2 * Kb) {
-      s.om[t256] = p.omega[size_t(n) * 2 * Kb + t256];
+    for (int i = t512; i < 4 * n_poly * Kb; i += EPI_THREADS) s.basis[i] = p.basis[i];
+    if (t512 < 2 * Kb) {
+      s.om[t512] = p.omega[size_t(n) * 2 * Kb + t512];
       if (GRAD) {
-        s.om[2 * MAX_KB + t256] = p.adam_m[size_t(n) * 2 * Kb + t256];
-        s.om[4 * MAX_KB + t256] = p.adam_v[size_t(n) * 2 * Kb + t256];
+        s.om[2 * MAX_KB + t512] = p.adam_m[size_t(n) * 2 * Kb + t512];
+        s.om[4 * MAX_KB + t512] = p.adam_v[size_t(n) * 2 * Kb + t512];
       }
     }
     const float2 pa = make_float2(p.a[2 * n], p.a[2 * n + 1]);
     const float2 pb = make_float2(p.b[2 * n], p.b[2 * n + 1]);
-    named_bar(3, 256);
+    // small weights (W1, b1, b2, b3) of this group's first decoder
+    if (chain_id < K && tg < 144) cp_async16(swbuf + tg * 4, dec_ptr(p.packed, chain_id) + tg * 4);
+    named_bar(3, EPI_THREADS);
 
     for (int step = 0; step < p.steps; ++step) {
-      if (t256 < 8 * n_poly) {
-        const int r = t256 >> 1, d = t256 & 1;
+      if (t512 < 8 * n_poly) {
+        const int r = t512 >> 1, d = t512 & 1;
         float acc = 0.f;
         for (int k = 0; k < Kb; ++k) acc = fmaf(s.basis[r * Kb + k], s.om[2 * k + d], acc);
-        s.coef[t256] = acc;
+        s.coef[t512] = acc;
       }
-      if (t256 < 2 * MAX_KB) s.gacc[t256] = 0.f;
-      float e_tot = 0.f, l_tot = 0.f;  // meaningful in t256 == 0
-      named_bar(3, 256);
+      if (t512 < 2 * MAX_KB) s.gacc[t512] = 0.f;
+      float e_tot = 0.f, l_tot = 0.f;  // meaningful in t512 == 0
+      named_bar(3, EPI_THREADS);
 
       for (int tile = 0; tile < ntiles; ++tile) {
         const int seg0 = tile * TILE_SEGS;
         const int nseg = min(TILE_SEGS, T - 1 - seg0);
         const int turn0 = (step * ntiles + tile) * K;
+        const bool last_tile = (step == p.steps - 1) && (tile == ntiles - 1);
         // ---- tile setup ----
-        if (wg == 0) {
+        if (chain_id == 0 && half == 0) {
           const int ti = min(seg0 + row, T - 1);
           const float t = p.t[ti];
           s.ts[row] = t;
           s.zs[row] = spline_point(t, n_poly, s.coef, pa, pb);
+        } else if (chain_id == 1 && half == 0) {
           if (p.draws != nullptr) {
             for (int m = 0; m < M; ++m)
               for (int role = 0; role < 2; ++role) {
@@ -271,197 +298,256 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p) {
             }
           }
         }
-        for (int i = t256; i < M * 128 * DIFF_STRIDE / 4; i += 256)
+        for (int i = t512; i < M * 128 * DIFF_STRIDE / 4; i += EPI_THREADS)
           reinterpret_cast<float4*>(s.Diff)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         float dzx = 0.f, dzy = 0.f;
-        named_bar(3, 256);
+        named_bar(3, EPI_THREADS);
         const float2 z = s.zs[row];
+        const float2 zx2 = make_float2(z.x, z.x), zy2 = make_float2(z.y, z.y);
 
         // =============================== forward ===============================
-        for (int k = wg; k < K; k += 2) {
-          const float* dec = dec_ptr(p.packed, k);
-          for (int i = row; i < 576; i += 128) sw[i] = __ldg(dec + i);
-          named_bar(1 + wg, 128);
-          // layer 1 (CUDA cores, fp32) -> A1 in X
-#pragma unroll 1
-          for (int c0 = 0; c0 < 128; c0 += 32) {
+        for (int k = chain_id; k < K; k += 2) {
+          // small weights of decoder k were prefetched into swbuf[swsel]; prefetch the next item's
+          cp_async_wait_all();
+          named_bar(bar_id, GROUP_THREADS);
+          const float* sw = swbuf + swsel * 576;
+          {
+            int kn = k + 2;
+            if (kn >= K) kn = GRAD ? chain_id : (last_tile ? -1 : chain_id);
+            if (kn >= 0 && kn < K && tg < 144)
+              cp_async16(swbuf + (swsel ^ 1) * 576 + tg * 4, dec_ptr(p.packed, kn) + tg * 4);
+          }
+          swsel ^= 1;
+          // layer 1 (CUDA cores, fp32) -> A1 in X[col0 : col0+64]
+#pragma unroll
+          for (int c0 = 0; c0 < 64; c0 += 32) {
             uint32_t v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int c = c0 + j;
-              const float h = fmaf(sw[OFF_W1 + 2 * c + 1], z.y, fmaf(sw[OFF_W1 + 2 * c], z.x, sw[OFF_B1 + c]));
-              v[j] = to_tf32(fmaxf(h, 0.f));
+            for (int j = 0; j < 32; j += 2) {
+              const int c = col0 + c0 + j;
+              const float2 wx = *reinterpret_cast<const float2*>(sw + OFF_W1X + c);
+              const float2 wy = *reinterpret_cast<const float2*>(sw + OFF_W1Y + c);
+              const float2 bb = *reinterpret_cast<const float2*>(sw + OFF_B1 + c);
+              const float2 h = ffma2(wy, zy2, ffma2(wx, zx2, bb));
+              v[j] = relu_tf32(h.x);
+              v[j + 1] = relu_tf32(h.y);
             }
-            tmem_st32(colX + c0, v);
+            tmem_st32(colX + col0 + c0, v);
           }
           tmem_wait_st();
           tc_fence_before();
-          mbar_arrive(&a_ready[wg]);
+          mbar_arrive(&a_ready[chain_id]);
           // layer 2 epilogue: D2 (Y) -> relu(+b2) -> A2 (Y, in place), mask bits
-          mbar_wait(&acc_ready[wg], ph_acc);
+          mbar_wait(&acc_ready[chain_id], ph_acc);
           ph_acc ^= 1;
           tc_fence_after();
-#pragma unroll 1
-          for (int c0 = 0; c0 < 128; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld32(colY + c0, v);
-            tmem_wait_ld();
-            uint32_t bits = 0;
+          {
+            uint32_t v0[32], v1[32];
+            tmem_ld32x2_sync(colY + col0, colY + col0 + 32, v0, v1);
+            uint32_t bits0 = 0, bits1 = 0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float h = __uint_as_float(v[j]) + sw[OFF_B2 + c0 + j];
-              if (h > 0.f) bits |= 1u << j;
-              v[j] = to_tf32(fmaxf(h, 0.f));
+            for (int j = 0; j < 32; j += 2) {
+              const float2 b0 = *reinterpret_cast<const float2*>(sw + OFF_B2 + col0 + j);
+              const float2 b1 = *reinterpret_cast<const float2*>(sw + OFF_B2 + col0 + 32 + j);
+              const float2 h0 = fadd2(make_float2(__uint_as_float(v0[j]), __uint_as_float(v0[j + 1])), b0);
+              const float2 h1 = fadd2(make_float2(__uint_as_float(v1[j]), __uint_as_float(v1[j + 1])), b1);
+              if (h0.x > 0.f) bits0 |= 1u << j;
+              if (h0.y > 0.f) bits0 |= 2u << j;
+              if (h1.x > 0.f) bits1 |= 1u << j;
+              if (h1.y > 0.f) bits1 |= 2u << j;
+              v0[j] = relu_tf32(h0.x);
+              v0[j + 1] = relu_tf32(h0.y);
+              v1[j] = relu_tf32(h1.x);
+              v1[j + 1] = relu_tf32(h1.y);
             }
-            tmem_st32(colY + c0, v);
-            if (GRAD) s.mask2[(k * 128 + row) * 4 + (c0 >> 5)] = bits;
+            tmem_st32(colY + col0, v0);
+            tmem_st32(colY + col0 + 32, v1);
+            if (GRAD)
+              *reinterpret_cast<uint2*>(s.mask2 + (k * 128 + row) * 4 + half * 2) = make_uint2(bits0, bits1);
           }
           tmem_wait_st();
           tc_fence_before();
-          mbar_arrive(&a_ready[wg]);
-          // layer 3 epilogue: D3 (X[0:64]) + b3 -> Diff
-          mbar_wait(&acc_ready[wg], ph_acc);
+          mbar_arrive(&a_ready[chain_id]);
+          // layer 3 epilogue: D3 (X[0:64]) + b3 -> Diff (this thread: columns xc0 .. xc0+31)
+          mbar_wait(&acc_ready[chain_id], ph_acc);
           ph_acc ^= 1;
           tc_fence_after();
-          uint32_t x0[32], x1[32];
-          tmem_ld32(colX, x0);
-          tmem_ld32(colX + 32, x1);
-          tmem_wait_ld();
-          // Diff is shared by both warpgroups: updates are serialised in decoder order
-          if ((row & 127) == 0) {
+          float x[32];
+          {
+            uint32_t xv[32];
+            tmem_ld32_sync(colX + xc0, xv);
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bb = *reinterpret_cast<const float4*>(sw + OFF_B3 + xc0 + j);
+              x[j] = __uint_as_float(xv[j]) + bb.x;
+              x[j + 1] = __uint_as_float(xv[j + 1]) + bb.y;
+              x[j + 2] = __uint_as_float(xv[j + 2]) + bb.z;
+              x[j + 3] = __uint_as_float(xv[j + 3]) + bb.w;
+            }
+          }
+          // Diff is shared by both groups: updates are serialised in decoder order
+          if (tg == 0) {
             while (*s.turn != turn0 + k) {
             }
             __threadfence_block();
           }
-          named_bar(1 + wg, 128);
+          named_bar(bar_id, GROUP_THREADS);
+          const int nq = half ? (DIFF_STRIDE - 32) / 4 : 8;  // float4 groups of this thread's columns
           // role 0: this point is the left end of its segment
           for (int m = 0; m < M; ++m)
             if (s.sel[(m * 2 + 0) * 128 + row] == k) {
-              float* d = s.Diff + (m * 128 + row) * DIFF_STRIDE;
+              float4* d = reinterpret_cast<float4*>(s.Diff + (m * 128 + row) * DIFF_STRIDE + xc0);
 #pragma unroll
-              for (int j = 0; j < 32; ++j) d[j] -= __uint_as_float(x0[j]) + sw[OFF_B3 + j];
-#pragma unroll
-              for (int j = 0; j < 20; ++j)
-                if (32 + j < X) d[32 + j] -= __uint_as_float(x1[j]) + sw[OFF_B3 + 32 + j];
+              for (int q = 0; q < 8; ++q)
+                if (q < nq) {
+                  float4 v = d[q];
+                  v.x -= x[4 * q]; v.y -= x[4 * q + 1]; v.z -= x[4 * q + 2]; v.w -= x[4 * q + 3];
+                  d[q] = v;
+                }
             }
-          named_bar(1 + wg, 128);
+          named_bar(bar_id, GROUP_THREADS);
           // role 1: this point is the right end of the previous segment
           if (row >= 1)
             for (int m = 0; m < M; ++m)
               if (s.sel[(m * 2 + 1) * 128 + row - 1] == k) {
-                float* d = s.Diff + (m * 128 + row - 1) * DIFF_STRIDE;
+                float4* d = reinterpret_cast<float4*>(s.Diff + (m * 128 + row - 1) * DIFF_STRIDE + xc0);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) d[j] += __uint_as_float(x0[j]) + sw[OFF_B3 + j];
-#pragma unroll
-                for (int j = 0; j < 20; ++j)
-                  if (32 + j < X) d[32 + j] += __uint_as_float(x1[j]) + sw[OFF_B3 + 32 + j];
+                for (int q = 0; q < 8; ++q)
+                  if (q < nq) {
+                    float4 v = d[q];
+                    v.x += x[4 * q]; v.y += x[4 * q + 1]; v.z += x[4 * q + 2]; v.w += x[4 * q + 3];
+                    d[q] = v;
+                  }
               }
           __threadfence_block();
-          named_bar(1 + wg, 128);
-          if ((row & 127) == 0) *s.turn = turn0 + k + 1;
+          named_bar(bar_id, GROUP_THREADS);
+          if (tg == 0) *s.turn = turn0 + k + 1;
         }
-        named_bar(3, 256);
+        named_bar(3, EPI_THREADS);
 
         // =============================== energy ===============================
+        // (columns >= X of a Diff row are never written and stay zero)
         {
           float e = 0.f, l = 0.f;
-          for (int idx = t256; idx < M * 128; idx += 256) {
+          for (int idx = t512; idx < M * 128; idx += EPI_THREADS) {
             const int r = idx & 127;
             if (r < nseg) {
-              const float* d = s.Diff + idx * DIFF_STRIDE;
+              const float4* d = reinterpret_cast<const float4*>(s.Diff + idx * DIFF_STRIDE);
               float q = 0.f;
-              for (int c = 0; c < X; ++c) q = fmaf(d[c], d[c], q);
+#pragma unroll
+              for (int c = 0; c < DIFF_STRIDE / 4; ++c) {
+                const float4 v = d[c];
+                q = fmaf(v.x, v.x, q); q = fmaf(v.y, v.y, q); q = fmaf(v.z, v.z, q); q = fmaf(v.w, v.w, q);
+              }
               e += q;
               l += sqrtf(q);
             }
           }
           e = warp_sum(e);
           l = warp_sum(l);
-          if (lane == 0) { s.red[80 + (warp - 2)] = e; s.red[88 + (warp - 2)] = l; }
+          if (lane == 0) { s.red[80 + ew] = e; s.red[96 + ew] = l; }
         }
 
         if (GRAD) {
           // =============================== backward ===============================
-          for (int k = wg; k < K; k += 2) {
-            const float* dec = dec_ptr(p.packed, k);
-            named_bar(1 + wg, 128);  // previous item's readers of sw are done
-            for (int i = row; i < 384; i += 128) sw[i] = __ldg(dec + i);
-            // G = dE/dx_k (this point) -> X[0:64]
-#pragma unroll 1
-            for (int c0 = 0; c0 < 64; c0 += 32) {
+          for (int k = chain_id; k < K; k += 2) {
+            cp_async_wait_all();
+            named_bar(bar_id, GROUP_THREADS);
+            const float* sw = swbuf + swsel * 576;
+            {
+              int kn = k + 2;
+              if (kn >= K) kn = last_tile ? -1 : chain_id;
+              if (kn >= 0 && kn < K && tg < 144)
+                cp_async16(swbuf + (swsel ^ 1) * 576 + tg * 4, dec_ptr(p.packed, kn) + tg * 4);
+            }
+            swsel ^= 1;
+            // G = dE/dx_k (this point), columns xc0 .. xc0+31 -> X[xc0 : xc0+32]
+            {
               float g[32];
 #pragma unroll
               for (int j = 0; j < 32; ++j) g[j] = 0.f;
+              const int nq = half ? (DIFF_STRIDE - 32) / 4 : 8;
               for (int m = 0; m < M; ++m) {
                 if (row >= 1 && s.sel[(m * 2 + 1) * 128 + row - 1] == k) {
-                  const float* d = s.Diff + (m * 128 + row - 1) * DIFF_STRIDE + c0;
+                  const float4* d = reinterpret_cast<const float4*>(s.Diff + (m * 128 + row - 1) * DIFF_STRIDE + xc0);
 #pragma unroll
-                  for (int j = 0; j < 32; ++j)
-                    if (c0 + j < DIFF_STRIDE) g[j] += d[j];
+                  for (int q = 0; q < 8; ++q)
+                    if (q < nq) {
+                      const float4 v = d[q];
+                      g[4 * q] += v.x; g[4 * q + 1] += v.y; g[4 * q + 2] += v.z; g[4 * q + 3] += v.w;
+                    }
                 }
                 if (s.sel[(m * 2 + 0) * 128 + row] == k) {
-                  const float* d = s.Diff + (m * 128 + row) * DIFF_STRIDE + c0;
+                  const float4* d = reinterpret_cast<const float4*>(s.Diff + (m * 128 + row) * DIFF_STRIDE + xc0);
 #pragma unroll
-                  for (int j = 0; j < 32; ++j)
-                    if (c0 + j < DIFF_STRIDE) g[j] -= d[j];
+                  for (int q = 0; q < 8; ++q)
+                    if (q < nq) {
+                      const float4 v = d[q];
+                      g[4 * q] -= v.x; g[4 * q + 1] -= v.y; g[4 * q + 2] -= v.z; g[4 * q + 3] -= v.w;
+                    }
                 }
               }
               uint32_t v[32];
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = (c0 + j < X) ? to_tf32(coefm * g[j]) : 0u;
-              tmem_st32(colX + c0, v);
+              for (int j = 0; j < 32; ++j) v[j] = tf32_round_bits(__float_as_uint(coefm * g[j]));
+              tmem_st32(colX + xc0, v);
             }
             tmem_wait_st();
             tc_fence_before();
-            mbar_arrive(&a_ready[wg]);
-            named_bar(1 + wg, 128);  // sw visible
+            mbar_arrive(&a_ready[chain_id]);
             // dh2 = (G W3) * mask2 -> A4 (Y, in place)
-            mbar_wait(&acc_ready[wg], ph_acc);
+            mbar_wait(&acc_ready[chain_id], ph_acc);
             ph_acc ^= 1;
             tc_fence_after();
-#pragma unroll 1
-            for (int c0 = 0; c0 < 128; c0 += 32) {
-              uint32_t v[32];
-              tmem_ld32(colY + c0, v);
-              tmem_wait_ld();
-              const uint32_t bits = s.mask2[(k * 128 + row) * 4 + (c0 >> 5)];
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = ((bits >> j) & 1u) ? to_tf32(__uint_as_float(v[j])) : 0u;
-              tmem_st32(colY + c0, v);
-            }
-            tmem_wait_st();
-            tc_fence_before();
-            mbar_arrive(&a_ready[wg]);
-            // dh1 = (dh2 W2) * mask1 (recomputed); dz += dh1 W1
-            mbar_wait(&acc_ready[wg], ph_acc);
-            ph_acc ^= 1;
-            tc_fence_after();
-#pragma unroll 1
-            for (int c0 = 0; c0 < 128; c0 += 32) {
-              uint32_t v[32];
-              tmem_ld32(colX + c0, v);
-              tmem_wait_ld();
+            {
+              uint32_t v0[32], v1[32];
+              tmem_ld32x2_sync(colY + col0, colY + col0 + 32, v0, v1);
+              const uint2 bits = *reinterpret_cast<const uint2*>(s.mask2 + (k * 128 + row) * 4 + half * 2);
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
-                const int c = c0 + j;
-                const float wa = sw[OFF_W1 + 2 * c], wb = sw[OFF_W1 + 2 * c + 1];
-                const float h = fmaf(wb, z.y, fmaf(wa, z.x, sw[OFF_B1 + c]));
-                if (h > 0.f) {
-                  dzx = fmaf(__uint_as_float(v[j]), wa, dzx);
-                  dzy = fmaf(__uint_as_float(v[j]), wb, dzy);
-                }
+                v0[j] = ((bits.x >> j) & 1u) ? tf32_round_bits(v0[j]) : 0u;
+                v1[j] = ((bits.y >> j) & 1u) ? tf32_round_bits(v1[j]) : 0u;
               }
+              tmem_st32(colY + col0, v0);
+              tmem_st32(colY + col0 + 32, v1);
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(&a_ready[chain_id]);
+            // dh1 = (dh2 W2) * mask1 (recomputed); dz += dh1 W1 over this thread's 64 hidden units
+            mbar_wait(&acc_ready[chain_id], ph_acc);
+            ph_acc ^= 1;
+            tc_fence_after();
+            {
+              uint32_t v0[32], v1[32];
+              tmem_ld32x2_sync(colX + col0, colX + col0 + 32, v0, v1);
+              float2 ax = make_float2(0.f, 0.f), ay = make_float2(0.f, 0.f);
+#pragma unroll
+              for (int j = 0; j < 64; j += 2) {
+                const int c = col0 + j;
+                const float2 wx = *reinterpret_cast<const float2*>(sw + OFF_W1X + c);
+                const float2 wy = *reinterpret_cast<const float2*>(sw + OFF_W1Y + c);
+                const float2 bb = *reinterpret_cast<const float2*>(sw + OFF_B1 + c);
+                const float2 h = ffma2(wy, zy2, ffma2(wx, zx2, bb));
+                const uint32_t r0 = j < 32 ? v0[j] : v1[j - 32];
+                const uint32_t r1 = j < 32 ? v0[j + 1] : v1[j - 31];
+                const float2 dh = make_float2(h.x > 0.f ? __uint_as_float(r0) : 0.f, h.y > 0.f ? __uint_as_float(r1) : 0.f);
+                ax = ffma2(dh, wx, ax);
+                ay = ffma2(dh, wy, ay);
+              }
+              dzx += ax.x + ax.y;
+              dzy += ay.x + ay.y;
             }
           }
-          s.dzs[wg * 128 + row] = make_float2(dzx, dzy);
+          s.dzs[(chain_id * 2 + half) * 128 + row] = make_float2(dzx, dzy);
         }
-        named_bar(3, 256);
+        named_bar(3, EPI_THREADS);
         // ---- d(omega) += P^T dz, energy partials ----
-        if (GRAD && wg == 0) {
+        if (GRAD && chain_id == 0 && half == 0) {
           float P[MAX_KB];
           design_row(s.ts[row], n_poly, Kb, s.basis, P);
-          const float2 d0 = s.dzs[row], d1 = s.dzs[128 + row];
-          const float dx = d0.x + d1.x, dy = d0.y + d1.y;
+          const float2 d0 = s.dzs[row], d1 = s.dzs[128 + row], d2 = s.dzs[256 + row], d3 = s.dzs[384 + row];
+          const float dx = (d0.x + d1.x) + (d2.x + d3.x), dy = (d0.y + d1.y) + (d2.y + d3.y);
 #pragma unroll
           for (int k = 0; k < MAX_KB; ++k)
             if (k < Kb) {
@@ -469,19 +555,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p) {
               if (lane == 0) { s.red[(warp & 3) * 20 + 2 * k] = cx; s.red[(warp & 3) * 20 + 2 * k + 1] = cy; }
             }
         }
-        if (t256 == 0) {
+        if (t512 == 0) {
           float ee = 0.f, ll = 0.f;
-          for (int w = 0; w < 8; ++w) { ee += s.red[80 + w]; ll += s.red[88 + w]; }
+          for (int w = 0; w < 16; ++w) { ee += s.red[80 + w]; ll += s.red[96 + w]; }
           e_tot += ee;
           l_tot += ll;
         }
-        named_bar(3, 256);
-        if (GRAD && t256 < 2 * Kb)
-          s.gacc[t256] += (s.red[t256] + s.red[20 + t256]) + (s.red[40 + t256] + s.red[60 + t256]);
+        named_bar(3, EPI_THREADS);
+        if (GRAD && t512 < 2 * Kb)
+          s.gacc[t512] += (s.red[t512] + s.red[20 + t512]) + (s.red[40 + t512] + s.red[60 + t512]);
       }  // tiles
 
-      named_bar(3, 256);
-      if (t256 == 0) {
+      named_bar(3, EPI_THREADS);
+      if (t512 == 0) {
         const float E = e_tot / float(M);
         if (p.energy_trace) p.energy_trace[size_t(step) * p.N + n] = E;
         if (step == p.steps - 1) {
@@ -489,28 +575,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p) {
           if (p.length_out) p.length_out[n] = l_tot / float(M);
         }
       }
-      if (GRAD && t256 < 2 * Kb) {
-        const int k = t256 >> 1, d = t256 & 1;
+      if (GRAD && t512 < 2 * Kb) {
+        const int k = t512 >> 1, d = t512 & 1;
         const float tend = p.t[T - 1];
         float P[MAX_KB];
         design_row(tend, n_poly, Kb, s.basis, P);
         const float2 ze = spline_point(tend, n_poly, s.coef, pa, pb);
         const float err = d == 0 ? ze.x - pb.x : ze.y - pb.y;
-        const float g = s.gacc[t256] + (2.0f * p.penalty_w) * err * P[k];
+        const float g = s.gacc[t512] + (2.0f * p.penalty_w) * err * P[k];
         AdamScalars sc = adam_scalars(p.step0 + step + 1, p.lr, p.beta1, p.beta2);
-        float om = s.om[t256], mm = s.om[2 * MAX_KB + t256], vv = s.om[4 * MAX_KB + t256];
+        float om = s.om[t512], mm = s.om[2 * MAX_KB + t512], vv = s.om[4 * MAX_KB + t512];
         adam_update(om, mm, vv, g, sc, p.one_minus_b1, p.beta2f, p.one_minus_b2, p.eps);
-        s.om[t256] = om;
-        s.om[2 * MAX_KB + t256] = mm;
-        s.om[4 * MAX_KB + t256] = vv;
+        s.om[t512] = om;
+        s.om[2 * MAX_KB + t512] = mm;
+        s.om[4 * MAX_KB + t512] = vv;
       }
-      named_bar(3, 256);
+      named_bar(3, EPI_THREADS);
     }  // steps
 
-    if (GRAD && t256 < 2 * Kb) {
-      p.omega[size_t(n) * 2 * Kb + t256] = s.om[t256];
-      p.adam_m[size_t(n) * 2 * Kb + t256] = s.om[2 * MAX_KB + t256];
-      p.adam_v[size_t(n) * 2 * Kb + t256] = s.om[4 * MAX_KB + t256];
+    cp_async_wait_all();
+    if (GRAD && t512 < 2 * Kb) {
+      p.omega[size_t(n) * 2 * Kb + t512] = s.om[t512];
+      p.adam_m[size_t(n) * 2 * Kb + t512] = s.om[2 * MAX_KB + t512];
+      p.adam_v[size_t(n) * 2 * Kb + t512] = s.om[4 * MAX_KB + t512];
     }
   }
 

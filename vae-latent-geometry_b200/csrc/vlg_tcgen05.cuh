@@ -68,7 +68,8 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
       : VLG_R8(v, 0), VLG_R8(v, 8)
       : "r"(taddr)
       : "memory");
@@ -79,6 +80,29 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
       : VLG_R8(v, 0), VLG_R8(v, 8), VLG_R8(v, 16), VLG_R8(v, 24)
       : "r"(taddr)
+      : "memory");
+}
+// Load + wait fused into ONE asm statement: the destination registers only become visible to
+// the compiler after tcgen05.wait::ld, so it cannot schedule their consumers before the wait
+// (separate asm statements do not order register uses -- that bit us once).
+__device__ __forceinline__ void tmem_ld32_sync(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : VLG_R8(v, 0), VLG_R8(v, 8), VLG_R8(v, 16), VLG_R8(v, 24)
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32x2_sync(uint32_t taddr0, uint32_t taddr1, uint32_t (&a)[32], uint32_t (&b)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%64];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%65];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : VLG_R8(a, 0), VLG_R8(a, 8), VLG_R8(a, 16), VLG_R8(a, 24), VLG_R8(b, 0), VLG_R8(b, 8), VLG_R8(b, 16), VLG_R8(b, 24)
+      : "r"(taddr0), "r"(taddr1)
       : "memory");
 }
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {

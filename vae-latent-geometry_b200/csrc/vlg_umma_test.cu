@@ -91,8 +91,7 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(const float* __restr
   tc_fence_after();
   for (int c0 = 0; c0 < NN; c0 += 16) {
     uint32_t v[16];
-    tmem_ld16(tmem + lane_base + colD + c0, v);
-    tmem_wait_ld();
+    tmem_ld16(tmem + lane_base + colD + c0, v);  // ld + wait in one asm statement
 #pragma unroll
     for (int j = 0; j < 16; ++j) D[size_t(tid) * NN + c0 + j] = __uint_as_float(v[j]);
   }
