@@ -24,6 +24,21 @@
 
 namespace vlg {
 
+#ifdef VLG_TC_STATS
+// debug build only: per-CTA wait-cycle counters [cta][8]
+__device__ long long g_tc_stats[1024 * 8];
+__device__ long long g_tc_phase[1024 * 16];
+#define PH_T0() long long _p0 = clock64()
+#define PH_ADD(i) do { long long _n = clock64(); ph_t[i] += _n - _p0; _p0 = _n; } while (0)
+#define STAT_T0() long long _t0 = clock64()
+#define STAT_ADD(var) var += clock64() - _t0
+#else
+#define STAT_T0()
+#define STAT_ADD(var)
+#define PH_T0()
+#define PH_ADD(i)
+#endif
+
 namespace {
 
 using namespace tc;
@@ -168,6 +183,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p) {
     if (lane == 0) {
       int slot = 0;
       uint32_t ph = 0;
+      long long w_empty = 0;
       for (long tl = 0; tl < total_tiles; ++tl)
         for (int phase = 0; phase < (GRAD ? 2 : 1); ++phase)
           for (int pr = 0; pr < npairs; ++pr)
@@ -178,12 +194,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p) {
                 const OpInfo oi = op_info(phase * 2 + o);
                 const char* src = reinterpret_cast<const char*>(dec_ptr(p.packed, k) + oi.img_off);
                 for (int st = 0; st < oi.nstages; ++st) {
-                  mbar_wait(&empty[slot], ph ^ 1);
+                  { STAT_T0(); mbar_wait(&empty[slot], ph ^ 1); STAT_ADD(w_empty); }
                   mbar_expect_tx(&full[slot], STAGE_BYTES);
                   bulk_g2s(s.ring + slot * STAGE_BYTES, src + size_t(st) * STAGE_BYTES, STAGE_BYTES, &full[slot]);
                   if (++slot == NSTAGES) { slot = 0; ph ^= 1; }
                 }
               }
+#ifdef VLG_TC_STATS
+      if (n < 1024) g_tc_stats[n * 8 + 0] = w_empty;
+#endif
+      (void)w_empty;
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
@@ -191,6 +211,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p) {
       int slot = 0;
       uint32_t ph = 0;
       uint32_t ph_a[2] = {0, 0};
+      long long w_a = 0, w_full = 0, w_issue = 0, w_commit = 0;
+      STAT_T0();
       for (long tl = 0; tl < total_tiles; ++tl)
         for (int phase = 0; phase < (GRAD ? 2 : 1); ++phase)
           for (int pr = 0; pr < npairs; ++pr)
@@ -201,25 +223,38 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p) {
                 const OpInfo oi = op_info(phase * 2 + o);
                 const uint32_t idesc = umma_idesc_tf32(oi.n, 0);
                 const uint32_t chain = tmem + uint32_t(c) * 256u;
-                mbar_wait(&a_ready[c], ph_a[c]);
+                { STAT_T0(); mbar_wait(&a_ready[c], ph_a[c]); STAT_ADD(w_a); }
                 ph_a[c] ^= 1;
                 tc_fence_after();
                 for (int st = 0; st < oi.nstages; ++st) {
-                  mbar_wait(&full[slot], ph);
+                  { STAT_T0(); mbar_wait(&full[slot], ph); STAT_ADD(w_full); }
                   tc_fence_after();
                   const uint32_t sbase = smem_u32(s.ring + slot * STAGE_BYTES);
                   const int nk = oi.kper / 8;
-                  for (int ks = 0; ks < nk; ++ks) {
-                    const uint64_t desc =
-                        umma_smem_desc(sbase + uint32_t(ks) * 2u * uint32_t(oi.n) * 16u, uint32_t(oi.n) * 16u, 128u);
-                    umma_tf32_ts(chain + oi.d_col, chain + oi.a_col + uint32_t(st * oi.kper + ks * 8), desc, idesc,
-                                 (st | ks) ? 1u : 0u);
+                  {
+                    STAT_T0();
+                    for (int ks = 0; ks < nk; ++ks) {
+                      const uint64_t desc =
+                          umma_smem_desc(sbase + uint32_t(ks) * 2u * uint32_t(oi.n) * 16u, uint32_t(oi.n) * 16u, 128u);
+                      umma_tf32_ts(chain + oi.d_col, chain + oi.a_col + uint32_t(st * oi.kper + ks * 8), desc, idesc,
+                                   (st | ks) ? 1u : 0u);
+                    }
+                    STAT_ADD(w_issue);
                   }
-                  umma_commit(&empty[slot]);
+                  {
+                    STAT_T0();
+                    umma_commit(&empty[slot]);
+                    STAT_ADD(w_commit);
+                  }
                   if (++slot == NSTAGES) { slot = 0; ph ^= 1; }
                 }
                 umma_commit(&acc_ready[c]);
               }
+#ifdef VLG_TC_STATS
+      if (n < 1024) { g_tc_stats[n * 8 + 1] = w_a; g_tc_stats[n * 8 + 2] = w_full; g_tc_stats[n * 8 + 3] = clock64() - _t0;
+                      g_tc_stats[n * 8 + 5] = w_issue; g_tc_stats[n * 8 + 7] = w_commit; }
+#endif
+      (void)w_a; (void)w_full; (void)w_issue; (void)w_commit;
     }
   } else {
     // ================= epilogue groups =================
@@ -239,6 +274,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p) {
     int swsel = 0;
     uint32_t ph_acc = 0;
     const float coefm = 2.0f / float(M);
+    long long w_acc = 0, w_turn = 0;
+    long long ph_t[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    (void)ph_t;
 
     for (int i = t512; i < 4 * n_poly * Kb; i += EPI_THREADS) s.basis[i] = p.basis[i];
     if (t512 < 2 * Kb) {
@@ -308,8 +346,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p) {
         // =============================== forward ===============================
         for (int k = chain_id; k < K; k += 2) {
           // small weights of decoder k were prefetched into swbuf[swsel]; prefetch the next item's
+          PH_T0();
           cp_async_wait_all();
           named_bar(bar_id, GROUP_THREADS);
+          PH_ADD(0);
           const float* sw = swbuf + swsel * 576;
           {
             int kn = k + 2;
@@ -334,16 +374,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p) {
             }
             tmem_st32(colX + col0 + c0, v);
           }
+          PH_ADD(1);
           tmem_wait_st();
           tc_fence_before();
           mbar_arrive(&a_ready[chain_id]);
+          PH_ADD(2);
           // layer 2 epilogue: D2 (Y) -> relu(+b2) -> A2 (Y, in place), mask bits
-          mbar_wait(&acc_ready[chain_id], ph_acc);
+          { STAT_T0(); mbar_wait(&acc_ready[chain_id], ph_acc); STAT_ADD(w_acc); }
           ph_acc ^= 1;
           tc_fence_after();
+          PH_ADD(3);
           {
             uint32_t v0[32], v1[32];
             tmem_ld32x2_sync(colY + col0, colY + col0 + 32, v0, v1);
+            PH_ADD(4);
             uint32_t bits0 = 0, bits1 = 0;
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
@@ -365,13 +409,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p) {
             if (GRAD)
               *reinterpret_cast<uint2*>(s.mask2 + (k * 128 + row) * 4 + half * 2) = make_uint2(bits0, bits1);
           }
+          PH_ADD(5);
           tmem_wait_st();
           tc_fence_before();
           mbar_arrive(&a_ready[chain_id]);
+          PH_ADD(6);
           // layer 3 epilogue: D3 (X[0:64]) + b3 -> Diff (this thread: columns xc0 .. xc0+31)
-          mbar_wait(&acc_ready[chain_id], ph_acc);
+          { STAT_T0(); mbar_wait(&acc_ready[chain_id], ph_acc); STAT_ADD(w_acc); }
           ph_acc ^= 1;
           tc_fence_after();
+          PH_ADD(7);
           float x[32];
           {
             uint32_t xv[32];
@@ -385,10 +432,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p) {
               x[j + 3] = __uint_as_float(xv[j + 3]) + bb.w;
             }
           }
+          PH_ADD(8);
           // Diff is shared by both groups: updates are serialised in decoder order
           if (tg == 0) {
+            STAT_T0();
             while (*s.turn != turn0 + k) {
             }
+            STAT_ADD(w_turn);
             __threadfence_block();
           }
           named_bar(bar_id, GROUP_THREADS);
@@ -422,6 +472,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p) {
           __threadfence_block();
           named_bar(bar_id, GROUP_THREADS);
           if (tg == 0) *s.turn = turn0 + k + 1;
+          PH_ADD(9);
         }
         named_bar(3, EPI_THREADS);
 
@@ -496,7 +547,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p) {
             tc_fence_before();
             mbar_arrive(&a_ready[chain_id]);
             // dh2 = (G W3) * mask2 -> A4 (Y, in place)
-            mbar_wait(&acc_ready[chain_id], ph_acc);
+            { STAT_T0(); mbar_wait(&acc_ready[chain_id], ph_acc); STAT_ADD(w_acc); }
             ph_acc ^= 1;
             tc_fence_after();
             {
@@ -515,7 +566,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p) {
             tc_fence_before();
             mbar_arrive(&a_ready[chain_id]);
             // dh1 = (dh2 W2) * mask1 (recomputed); dz += dh1 W1 over this thread's 64 hidden units
-            mbar_wait(&acc_ready[chain_id], ph_acc);
+            { STAT_T0(); mbar_wait(&acc_ready[chain_id], ph_acc); STAT_ADD(w_acc); }
             ph_acc ^= 1;
             tc_fence_after();
             {
@@ -594,6 +645,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p) {
     }  // steps
 
     cp_async_wait_all();
+#ifdef VLG_TC_STATS
+    if (tg == 0 && n < 1024) { g_tc_stats[n * 8 + 4 + chain_id * 2] = w_acc; if (chain_id == 0) for (int i = 0; i < 16; ++i) g_tc_phase[n * 16 + i] = ph_t[i]; }
+#endif
+    (void)w_acc; (void)w_turn;
     if (GRAD && t512 < 2 * Kb) {
       p.omega[size_t(n) * 2 * Kb + t512] = s.om[t512];
       p.adam_m[size_t(n) * 2 * Kb + t512] = s.om[2 * MAX_KB + t512];
@@ -607,6 +662,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p) {
 }
 
 size_t tc_workspace_bytes(int, int, int, int) { return 0; }
+
+#ifdef VLG_TC_STATS
+extern "C" int vlg_debug_tc_stats(long long* host_out, int n) {
+  return cudaMemcpyFromSymbol(host_out, g_tc_stats, size_t(n) * 8 * sizeof(long long)) == cudaSuccess ? 0 : -3;
+}
+extern "C" int vlg_debug_tc_phase(long long* host_out, int n) {
+  return cudaMemcpyFromSymbol(host_out, g_tc_phase, size_t(n) * 16 * sizeof(long long)) == cudaSuccess ? 0 : -3;
+}
+#endif
 
 cudaError_t launch_tc(const StepParams& p, bool grad, cudaStream_t stream) {
   if (p.precision != 1) return cudaErrorNotSupported;  // 3xTF32 not built yet

@@ -121,3 +121,75 @@ extern "C" int vlg_selftest_umma_ex(const float* A, const float* Bimg, const flo
   vlg::umma_selftest_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(A, Bimg, Blo, D, N, K, b_mn_major, split3, lbo, sbo, kstep);
   return cudaGetLastError() == cudaSuccess ? VLG_OK : VLG_ERR_CUDA;
 }
+
+// ---- tensor-pipe rate probe: `iters` back-to-back kind::tf32 MMAs (M=128, K=8, A in TMEM,
+// B in shared memory), one commit at the end; reports clock64 cycles per CTA. ----
+namespace vlg {
+namespace {
+__global__ void __launch_bounds__(384) mma_rate_kernel(int N, int iters, int lbo, int sbo, int mode, long long* out) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bar_mma;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ volatile int done;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 144 * 128; i += blockDim.x) reinterpret_cast<float*>(smem)[i] = 1.0f;
+  if (tid == 0) {
+    tc::mbar_init(&bar_mma, 1);
+    tc::fence_mbar_init();
+    done = 0;
+  }
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
+  tc::fence_proxy_async();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  if (tid == 0) {
+    const uint32_t idesc = tc::umma_idesc_tf32(N, 0);
+    const uint32_t sb = tc::smem_u32(smem);
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+      const int ks = i & 7;
+      const uint64_t desc = tc::umma_smem_desc(sb + uint32_t(ks) * 2u * uint32_t(lbo), uint32_t(lbo), uint32_t(sbo));
+      tc::umma_tf32_ts(tmem + 128u, tmem + uint32_t(ks) * 8u, desc, idesc, 1u);
+    }
+    tc::umma_commit(&bar_mma);
+    tc::mbar_wait(&bar_mma, 0);
+    out[blockIdx.x] = clock64() - t0;
+    done = 1;
+  } else if (warp >= 4) {
+    // interference generators: mode bit0 = TMEM ld/st traffic (columns 384..447), bit1 = shared-memory loads
+    const uint32_t lane_addr = uint32_t((warp & 3) * 32) << 16;
+    float acc = 0.f;
+    while (!done) {
+      if (mode & 1) {
+        uint32_t v[32];
+        tc::tmem_ld32_sync(tmem + lane_addr + 384u + uint32_t((warp >> 2) & 1) * 32u, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += 1u;
+        tc::tmem_st32(tmem + lane_addr + 384u + uint32_t((warp >> 2) & 1) * 32u, v);
+        tc::tmem_wait_st();
+      }
+      if (mode & 2) {
+        const float4* p4 = reinterpret_cast<const float4*>(smem) + (tid & 31);
+#pragma unroll
+        for (int j = 0; j < 64; ++j) { float4 q = p4[j * 32]; acc += q.x + q.y + q.z + q.w; }
+      }
+      if (mode == 0) break;
+    }
+    if (acc == 123.456f) out[0] = 0;
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+}  // namespace
+}  // namespace vlg
+
+extern "C" int vlg_selftest_mma_rate(int N, int iters, int lbo, int sbo, int ctas, int mode, long long* out, void* stream) {
+  const size_t smem = 144 * 128 * 4;
+  cudaError_t e = cudaFuncSetAttribute(vlg::mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  if (e != cudaSuccess) return VLG_ERR_CUDA;
+  vlg::mma_rate_kernel<<<ctas, 384, smem, static_cast<cudaStream_t>(stream)>>>(N, iters, lbo, sbo, mode, out);
+  return cudaGetLastError() == cudaSuccess ? VLG_OK : VLG_ERR_CUDA;
+}
