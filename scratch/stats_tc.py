@@ -1,5 +1,5 @@
 import sys, os, ctypes
-os.environ["VLG_B200_LIB"] = "scratch/libvlg_stats.so"
+os.environ["VLG_B200_LIB"] = sys.argv[1]
 sys.path.insert(0, ".")
 import numpy as np, torch
 import vlg_b200, bench
@@ -19,16 +19,20 @@ out = (ctypes.c_longlong * (nc * 8))()
 lib.vlg_debug_tc_stats.argtypes = [ctypes.c_void_p, ctypes.c_int]
 assert lib.vlg_debug_tc_stats(out, nc) == 0
 st = np.array(out).reshape(nc, 8).astype(np.float64)
-names = ["producer wait empty", "mma wait a_ready", "mma wait full", "mma total", "epi0 wait acc", "mma issue loops", "epi1 wait acc", "mma commits"]
+names = ["-", "-", "mma wait full", "mma total", "epi0 wait acc", "mma issue loops", "epi1 wait acc", "-"]
 for i, nm in enumerate(names):
-    print(f"{nm:22s} mean {st[:, i].mean():12.0f} cycles  ({100 * st[:, i].mean() / st[:, 3].mean():5.1f}% of mma total)")
+    if nm != "-":
+        print(f"{nm:22s} mean {st[:, i].mean():12.0f} cycles  ({100 * st[:, i].mean() / st[:, 3].mean():5.1f}% of mma total)")
 
-ph = (ctypes.c_longlong * (nc * 16))()
+ph = (ctypes.c_longlong * (nc * 24))()
 lib.vlg_debug_tc_phase.argtypes = [ctypes.c_void_p, ctypes.c_int]
 assert lib.vlg_debug_tc_phase(ph, nc) == 0
-ph = np.array(ph).reshape(nc, 16).astype(np.float64).mean(0)
-items = 16 * 5  # fwd items of chain 0 per curve-step
-names = ["sw wait+bar", "F1 compute+st", "F1 wait_st+arrive", "wait acc F2", "E-F2 tmem ld", "E-F2 compute+st", "E-F2 wait_st+arrive", "wait acc F3", "E-F3 ld+bias", "turn+Diff update"]
-for i, nm in enumerate(names):
-    print(f"fwd phase {nm:22s} {ph[i] / items:8.0f} cycles per item")
-print("fwd item total", sum(ph[:10]) / items)
+ph = np.array(ph).reshape(nc, 24).astype(np.float64).mean(0)
+items = 16 * 5 * 3  # items of chain 0 over the 3 launches (2 warm-up + 1)
+names = {0: "F sw wait+bar", 1: "F1 compute+st", 2: "F1 wait_st+arrive", 3: "wait acc F2", 4: "E-F2 tmem ld", 5: "E-F2 compute+st",
+         6: "E-F2 wait_st+arrive", 7: "wait acc F3", 8: "E-F3 ld+store", 10: "B sw wait+bar", 11: "G build+st", 12: "G wait_st+arrive",
+         13: "wait acc B3", 14: "E-B3 ld+mask+st", 15: "E-B3 wait_st+arrive", 16: "wait acc B2", 17: "E-B2 ld+dz"}
+tot = 0
+for i, nm in names.items():
+    print(f"phase {nm:22s} {ph[i] / items:8.0f} cycles per item"); tot += ph[i] / items
+print("item total (fwd+bwd)", tot)

@@ -3,34 +3,25 @@
 // Persistent CTAs (one per SM, 608 threads), each walking a strided list of curves; per curve
 // all `steps` Adam steps run inside the kernel.  The two 128-wide decoder layers and their
 // transposes run as tcgen05.mma kind::tf32 with
-//   * M = 128 rows = the 128 TMEM lanes,
+//   * M = 128 curve points = the 128 TMEM lanes,
 //   * the A operand (activations) living in TENSOR MEMORY: the epilogue threads write the
 //     next layer's input back with tcgen05.st, in place of the accumulator they just read,
 //   * the B operand (weights) streamed from L2 into per-chain shared-memory rings by the TMA
 //     engine (1-D bulk copies of pre-packed no-swizzle K-major images, mbarrier complete_tx),
 //   * fp32 accumulators in TMEM, read back with tcgen05.ld.
-//
-// ROW COMPACTION.  The MC energy touches, per curve point, only the decoders drawn for the two
-// segments that meet there (<= 2M of K; 3.4 of 10 on average), and the reference's dense
-// K x T forward/backward spends two thirds of its FLOPs on outputs that are multiplied by zero.
-// Here a curve is cut into windows of 256 points (255 segments); for every decoder the points
-// of the window that drew it are gathered into the rows of one 128-row MMA tile ("item"; a
-// decoder drawn by more than 128 points simply gets several items).  Results are identical:
-// each selected (point, decoder) pair goes through exactly the same arithmetic.
-//
 // Warp roles: warps 0/1 = weight producers of chain 0/1 (one lane each), warp 2 = MMA issuer
 // (one lane), warps 3-10 and 11-18 = two epilogue groups of 8 warps.  Each group owns a "chain"
-// of 256 TMEM columns and every other item.  The MMA issuer serves whichever chain has its
-// operand ready, which is why every chain has its own weight ring.  Inside a group two threads
-// share a row (TMEM lane) and split its columns: four epilogue warps per scheduler hide TMEM /
-// shared-memory latency.
+// of 256 TMEM columns and every other decoder.  The MMA issuer serves whichever chain has its
+// operand ready (no fixed order, so a slow chain never blocks the other), which is why every
+// chain has its own weight ring.  Inside a group two threads share a curve point (TMEM lane)
+// and split its columns: four epilogue warps per scheduler hide TMEM / shared-memory latency.
 //
-// Per window: draws -> per-decoder row lists (shared-memory atomics; row order does not affect
-// any result) -> forward items (layer 1 on CUDA cores, exact fp32) -> selected outputs stored
-// with plain stores, one writer per slot (left-end output x1 of a segment in shared memory,
-// right-end output x2 in an L2-resident workspace) -> one pass forms x2-x1 and the energy ->
-// backward items (input gradient only; layer-2 ReLU masks as bits in the workspace, layer-1
-// mask recomputed) -> dz per point -> d(omega).  Penalty gradient and Adam as in vlg_simt.cu.
+// Per 128-point tile: forward of all K decoders (layer 1 on CUDA cores, exact fp32) -> the
+// selected decoder outputs are stored with plain stores, exactly one writer per slot: the
+// left-end output x1 of a segment into shared memory, the right-end output x2 into an
+// L2-resident workspace -> one pass forms x2-x1 in shared memory and the energy -> backward of
+// all K decoders (input gradient only; layer-2 ReLU masks as bits in the workspace, layer-1
+// mask recomputed) -> dz -> d(omega).  Penalty gradient and Adam as in vlg_simt.cu.
 #include "vlg_common.cuh"
 #include "vlg_kernels.h"
 #include "vlg_tcgen05.cuh"
@@ -40,11 +31,16 @@ namespace vlg {
 #ifdef VLG_TC_STATS
 // debug build only: per-CTA wait-cycle counters [cta][8]
 __device__ long long g_tc_stats[1024 * 8];
+__device__ long long g_tc_phase[1024 * 24];
+#define PH_T0() long long _p0 = clock64()
+#define PH_ADD(i) do { long long _n = clock64(); ph_t[i] += _n - _p0; _p0 = _n; } while (0)
 #define STAT_T0() long long _t0 = clock64()
 #define STAT_ADD(var) var += clock64() - _t0
 #else
 #define STAT_T0()
 #define STAT_ADD(var)
+#define PH_T0()
+#define PH_ADD(i)
 #endif
 
 namespace {
@@ -58,11 +54,6 @@ constexpr int FIRST_EPI_WARP = 3;
 constexpr int STAGE_BYTES = 16384;
 constexpr int MAX_STAGES = 4;         // per chain
 constexpr int XD_STRIDE = 52;         // floats per stored decoder output row (X <= 52; 16 B rows)
-constexpr int WIN_PTS = 256;          // curve points per window
-constexpr int WIN_SEGS = 255;         // segments per window: neighbouring windows share one point
-constexpr int TC_MAX_M = 2;           // MC samples supported by this kernel (shared-memory budget)
-constexpr int TC_MAX_K = 64;          // decoders
-constexpr int MAX_ITEMS = TC_MAX_K + 8;  // sum_k ceil(n_k/128) <= K + 4*256/128
 
 // the four tensor-core GEMMs of one decoder
 struct OpInfo {
@@ -108,67 +99,52 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 
-struct WinCtl {
-  int nitems;
-  int pad;
-  uint16_t item[MAX_ITEMS];  // decoder | pass << 8
-};
-
 struct TcSmem {
   unsigned char* ring;  // [chain][stage] 16 KB
-  float* XD;            // [m][256][52]: left-end outputs x1, then (after the energy pass) x2 - x1
-  uint8_t* sel;         // [m][role][256] drawn decoder per segment
-  uint8_t* rows;        // [K][256] points of the window that drew decoder k
-  int* cnt;             // [K]
-  WinCtl* ctl;          // [2] item lists, double buffered by window parity
+  float* XD;            // [m][128][52]: role-0 outputs, then (after the energy pass) x2 - x1
+  uint8_t* sel;         // MAX_M*2*128
   float* sw;            // [chain][buf] 576 floats
-  float2* zs;           // 256 latent points of the window
-  float2* dzs;          // [chain][half][256]
+  float2* zs;           // 128
+  float* ts;            // 128
+  float2* dzs;          // 4*128
   float* coef;          // 64
   float* basis;         // 288
   float* om;            // 56
   float* gacc;          // 20
-  float* red;           // 8*20 + 32
-  uint64_t* bars;       // full[2][MAX_STAGES], empty[2][MAX_STAGES], a_ready[2], acc_ready[2], win_ready
+  float* red;           // 4*20 + 32
+  uint64_t* bars;       // full[2][MAX_STAGES], empty[2][MAX_STAGES], a_ready[2], acc_ready[2]
   uint32_t* tmem_base;
 };
 
-constexpr int CTL_FLOATS = (2 * sizeof(WinCtl) + 3) / 4;
-constexpr int BAR_WORDS = 2 * (4 * MAX_STAGES + 5);
-
-__device__ __forceinline__ TcSmem tc_carve(unsigned char* base, int M, int K, int nst) {
+__device__ __forceinline__ TcSmem tc_carve(unsigned char* base, int M, int nst) {
   TcSmem s;
   s.ring = base;
   float* f = reinterpret_cast<float*>(base + 2 * nst * STAGE_BYTES);
-  s.XD = f; f += M * WIN_PTS * XD_STRIDE;
+  s.XD = f; f += M * 128 * XD_STRIDE;
   s.sw = f; f += 4 * 576;
-  s.zs = reinterpret_cast<float2*>(f); f += 2 * WIN_PTS;
-  s.dzs = reinterpret_cast<float2*>(f); f += 2 * 4 * WIN_PTS;
+  s.zs = reinterpret_cast<float2*>(f); f += 256;
+  s.ts = f; f += 128;
+  s.dzs = reinterpret_cast<float2*>(f); f += 1024;
   s.coef = f; f += 64;
   s.basis = f; f += 4 * MAX_NPOLY * MAX_KB;
   s.om = f; f += 3 * 2 * MAX_KB + 2;
   s.gacc = f; f += 2 * MAX_KB + 2;
-  s.red = f; f += 192;
-  s.bars = reinterpret_cast<uint64_t*>(f); f += BAR_WORDS;
+  s.red = f; f += 112;
+  s.bars = reinterpret_cast<uint64_t*>(f); f += 2 * (4 * MAX_STAGES + 4);
   s.tmem_base = reinterpret_cast<uint32_t*>(f); f += 4;
-  s.ctl = reinterpret_cast<WinCtl*>(f); f += CTL_FLOATS;
-  s.cnt = reinterpret_cast<int*>(f); f += TC_MAX_K;
-  s.sel = reinterpret_cast<uint8_t*>(f); f += TC_MAX_M * 2 * WIN_PTS / 4;
-  s.rows = reinterpret_cast<uint8_t*>(f);
-  (void)K;
+  s.sel = reinterpret_cast<uint8_t*>(f);
   return s;
 }
 
 }  // namespace
 
-static size_t tc_smem_fixed_bytes(int M, int K) {
-  size_t fl = size_t(M) * WIN_PTS * XD_STRIDE + 4 * 576 + 2 * WIN_PTS + 2 * 4 * WIN_PTS + 64 + 4 * MAX_NPOLY * MAX_KB +
-              (3 * 2 * MAX_KB + 2) + (2 * MAX_KB + 2) + 192 + BAR_WORDS + 4 + CTL_FLOATS + TC_MAX_K +
-              TC_MAX_M * 2 * WIN_PTS / 4;
-  return fl * 4 + size_t(K) * WIN_PTS;
+static size_t tc_smem_fixed_bytes(int M) {
+  size_t fl = size_t(M) * 128 * XD_STRIDE + 4 * 576 + 256 + 128 + 1024 + 64 + 4 * MAX_NPOLY * MAX_KB +
+              (3 * 2 * MAX_KB + 2) + (2 * MAX_KB + 2) + 112 + 2 * (4 * MAX_STAGES + 4) + 4 + MAX_M * 2 * 128 / 4;
+  return fl * 4;
 }
-static int tc_stages(int M, int K) {
-  const long budget = 232448 - long(tc_smem_fixed_bytes(M, K));
+static int tc_stages(int M) {
+  const long budget = 232448 - long(tc_smem_fixed_bytes(M));
   long nst = budget / (2 * STAGE_BYTES);
   if (nst > MAX_STAGES) nst = MAX_STAGES;
   return int(nst);
@@ -179,15 +155,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int M = p.M, K = p.K, T = p.T, n_poly = p.n_poly, Kb = p.Kb;
-  TcSmem s = tc_carve(smem_raw, M, K, nst);
+  TcSmem s = tc_carve(smem_raw, M, nst);
   uint64_t* full = s.bars;                       // [2][MAX_STAGES]
   uint64_t* empty = s.bars + 2 * MAX_STAGES;     // [2][MAX_STAGES]
   uint64_t* a_ready = s.bars + 4 * MAX_STAGES;
   uint64_t* acc_ready = s.bars + 4 * MAX_STAGES + 2;
-  uint64_t* win_ready = s.bars + 4 * MAX_STAGES + 4;
-  const int nwin = (T - 1 + WIN_SEGS - 1) / WIN_SEGS;
+  const int ntiles = (T - 1 + TILE_SEGS - 1) / TILE_SEGS;
   const int ncurves = (p.N - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);  // curves of this CTA
-  const long total_win = long(ncurves) * p.steps * nwin;
+  const long total_tiles = long(ncurves) * p.steps * ntiles;
 
   if (tid == 0) {
     for (int i = 0; i < 2 * MAX_STAGES; ++i) {
@@ -198,7 +173,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
     mbar_init(&a_ready[1], GROUP_THREADS);
     mbar_init(&acc_ready[0], 1);
     mbar_init(&acc_ready[1], 1);
-    mbar_init(win_ready, 1);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(s.tmem_base, 512);
@@ -207,29 +181,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
   tc_fence_after();
   const uint32_t tmem = *s.tmem_base;
 
-  // Item i of a window (decoder k, rows 128q..128q+127 of k's row list) belongs to chain i & 1.
-  // Per chain the tensor-core ops of a window are: for each of its items F2 F3, then (GRAD) for
-  // each of its items B3 B2.  The item list of window w is published in ctl[w & 1] and
-  // announced through the win_ready mbarrier (phase = w).
+  // Per chain c the sequence of tensor-core ops of a tile is fixed: for each of its decoders
+  // k = c, c+2, ...: F2(k) F3(k); then (GRAD) for each decoder: B3(k) B2(k).
   if (warp < 2) {
     // ================= weight producer of chain `warp` (TMA bulk copies) =================
     if (lane == 0) {
       const int c = warp;
+      const int ndec = (K - c + 1) / 2;
       uint64_t* fullc = full + c * MAX_STAGES;
       uint64_t* emptyc = empty + c * MAX_STAGES;
       unsigned char* ringc = s.ring + c * nst * STAGE_BYTES;
       int slot = 0;
       uint32_t ph = 0;
-      for (long w = 0; w < total_win; ++w) {
-        mbar_wait(win_ready, uint32_t(w & 1));
-        const WinCtl* ctl = &s.ctl[w & 1];
-        const int nit = ctl->nitems;
+      for (long tl = 0; tl < total_tiles; ++tl)
         for (int phase = 0; phase < (GRAD ? 2 : 1); ++phase)
-          for (int i = c; i < nit; i += 2) {
-            const int k = ctl->item[i] & 0xFF;
+          for (int kd = 0; kd < ndec; ++kd)
             for (int o = 0; o < 2; ++o) {
               const OpInfo oi = op_info(phase * 2 + o);
-              const char* src = reinterpret_cast<const char*>(dec_ptr(p.packed, k) + oi.img_off);
+              const char* src = reinterpret_cast<const char*>(dec_ptr(p.packed, c + 2 * kd) + oi.img_off);
               for (int st = 0; st < oi.nstages; ++st) {
                 mbar_wait(&emptyc[slot], ph ^ 1);
                 mbar_expect_tx(&fullc[slot], STAGE_BYTES);
@@ -237,37 +206,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                 if (++slot == nst) { slot = 0; ph ^= 1; }
               }
             }
-          }
-      }
     }
   } else if (warp == 2) {
     // ================= MMA issuer: serves whichever chain is ready =================
     if (lane == 0) {
-      int slot[2] = {0, 0}, opi[2] = {0, 0}, nitc[2] = {0, 0};
-      int ops_left[2] = {0, 0};      // ops of the chain's current window still to issue
-      long win[2] = {0, 0};          // next window whose item list the chain has to pick up
+      int slot[2] = {0, 0}, kd[2] = {0, 0}, opi[2] = {0, 0}, phase[2] = {0, 0};
       uint32_t ph[2] = {0, 0}, ph_a[2] = {0, 0};
+      long tiles_left[2];
+      const int ndec[2] = {(K + 1) / 2, K / 2};
+      tiles_left[0] = total_tiles;
+      tiles_left[1] = ndec[1] > 0 ? total_tiles : 0;
       long long w_full = 0, w_issue = 0;
       STAT_T0();
-      while (win[0] < total_win || ops_left[0] > 0 || win[1] < total_win || ops_left[1] > 0) {
+      int nap = 0;
+      while (tiles_left[0] > 0 || tiles_left[1] > 0) {
+        // nothing was ready in the last sweep: sleep on one chain's barrier (hardware-suspended
+        // try_wait) instead of burning issue slots, alternating the chain we sleep on
+#ifdef VLG_TC_NAP
+        if (nap) {
+          const int c = (nap & 1) && tiles_left[1] > 0 ? 1 : (tiles_left[0] > 0 ? 0 : 1);
+          (void)mbar_try_wait(&a_ready[c], ph_a[c]);
+        }
+#endif
+        ++nap;
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-          if (ops_left[c] == 0) {
-            if (win[c] >= total_win) continue;
-            if (!mbar_test(win_ready, uint32_t(win[c] & 1))) continue;
-            const int nit = s.ctl[win[c] & 1].nitems;
-            nitc[c] = (nit - c + 1) / 2;  // items of this chain in the window
-            ops_left[c] = nitc[c] * (GRAD ? 4 : 2);
-            opi[c] = 0;
-            ++win[c];
-            if (ops_left[c] == 0) continue;
-          }
+          if (tiles_left[c] <= 0) continue;
           if (!mbar_test(&a_ready[c], ph_a[c])) continue;
+          nap = 0;
           ph_a[c] ^= 1;
           tc_fence_after();
-          // op order inside a window: F2 F3 per item, then B3 B2 per item
-          const int optype = (opi[c] < 2 * nitc[c]) ? (opi[c] & 1) : 2 + ((opi[c] - 2 * nitc[c]) & 1);
-          const OpInfo oi = op_info(optype);
+          const OpInfo oi = op_info(phase[c] * 2 + opi[c]);
           const uint32_t idesc = umma_idesc_tf32(oi.n, 0);
           const uint32_t chain = tmem + uint32_t(c) * 256u;
           uint64_t* fullc = full + c * MAX_STAGES;
@@ -292,8 +261,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
             if (++slot[c] == nst) { slot[c] = 0; ph[c] ^= 1; }
           }
           umma_commit(&acc_ready[c]);
-          ++opi[c];
-          --ops_left[c];
+          // advance this chain's op cursor
+          if (++opi[c] == 2) {
+            opi[c] = 0;
+            if (++kd[c] == ndec[c]) {
+              kd[c] = 0;
+              if (++phase[c] == (GRAD ? 2 : 1)) {
+                phase[c] = 0;
+                --tiles_left[c];
+              }
+            }
+          }
         }
       }
 #ifdef VLG_TC_STATS
@@ -310,7 +288,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
     const int ew = warp - FIRST_EPI_WARP;       // 0..15
     const int chain_id = ew >> 3;               // group / chain
     const int half = (ew >> 2) & 1;             // which 64 of the 128 columns
-    const int row = (warp & 3) * 32 + lane;     // TMEM lane = row of the item
+    const int row = (warp & 3) * 32 + lane;     // TMEM lane = curve point of the tile
     const int tg = half * 128 + row;            // 0..255 inside the group
     const int t512 = chain_id * 256 + tg;       // 0..511 over both groups
     const uint32_t lane_addr = uint32_t((warp & 3) * 32) << 16;
@@ -325,16 +303,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
     uint32_t ph_acc = 0;
     const float coefm = 2.0f / float(M);
     long long w_acc = 0;
-    long wcount = 0;                            // windows processed by this CTA so far
-    // this CTA's slice of the L2-resident workspace: layer-2 ReLU masks [item][row][4 words], then
-    // the right-end decoder outputs x2 [m][256][52]
-    const size_t ws_cta = size_t(K + 8) * 512 + size_t(M) * WIN_PTS * XD_STRIDE;  // 32-bit words per CTA
+    long long ph_t[24] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    (void)ph_t;
+    // this CTA's slice of the L2-resident workspace: layer-2 ReLU masks [k][row][4 words], then
+    // the right-end decoder outputs x2 [m][128][52]
+    const size_t ws_cta = size_t(K) * 512 + size_t(M) * 128 * XD_STRIDE;  // 32-bit words per CTA
     uint32_t* maskws = reinterpret_cast<uint32_t*>(p.workspace) + size_t(blockIdx.x) * ws_cta;
-    float* X2 = reinterpret_cast<float*>(maskws + size_t(K + 8) * 512);
+    float* X2 = reinterpret_cast<float*>(maskws + size_t(K) * 512);
 
     for (int i = t512; i < 4 * n_poly * Kb; i += EPI_THREADS) s.basis[i] = p.basis[i];
+    // small weights (W1, b1, b2, b3) of this group's first decoder
+    if (chain_id < K && tg < 144) cp_async16(swbuf + tg * 4, dec_ptr(p.packed, chain_id) + tg * 4);
 
-    for (int n = blockIdx.x; n < p.N; n += gridDim.x) {
+    for (int n = blockIdx.x, ci = 0; n < p.N; n += gridDim.x, ++ci) {
+      const bool last_curve = (ci == ncurves - 1);
       if (t512 < 2 * Kb) {
         s.om[t512] = p.omega[size_t(n) * 2 * Kb + t512];
         if (GRAD) {
@@ -357,124 +339,93 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
         float e_tot = 0.f, l_tot = 0.f;  // meaningful in t512 == 0
         named_bar(3, EPI_THREADS);
 
-        for (int win = 0; win < nwin; ++win, ++wcount) {
-          const int seg0 = win * WIN_SEGS;
-          const int nseg = min(WIN_SEGS, T - 1 - seg0);
-          WinCtl* ctl = &s.ctl[wcount & 1];
-          // ---- window setup: points, draws, accumulators ----
-          if (t512 < WIN_PTS) {
-            const int pt = t512;
-            const int ti = min(seg0 + pt, T - 1);
-            s.zs[pt] = spline_point(p.t[ti], n_poly, s.coef, pa, pb);
+        for (int tile = 0; tile < ntiles; ++tile) {
+          const int seg0 = tile * TILE_SEGS;
+          const int nseg = min(TILE_SEGS, T - 1 - seg0);
+          const bool last_tile = last_curve && (step == p.steps - 1) && (tile == ntiles - 1);
+          // ---- tile setup ----
+          if (chain_id == 0 && half == 0) {
+            const int ti = min(seg0 + row, T - 1);
+            const float t = p.t[ti];
+            s.ts[row] = t;
+            s.zs[row] = spline_point(t, n_poly, s.coef, pa, pb);
+          } else if (chain_id == 1 && half == 0) {
             if (p.draws != nullptr) {
               for (int m = 0; m < M; ++m)
                 for (int role = 0; role < 2; ++role) {
                   uint8_t v = 255;
-                  if (pt < nseg)
-                    v = p.draws[(((size_t(n) * p.steps + step) * M + m) * 2 + role) * size_t(T - 1) + seg0 + pt];
-                  s.sel[(m * 2 + role) * WIN_PTS + pt] = v;
+                  if (row < nseg)
+                    v = p.draws[(((size_t(n) * p.steps + step) * M + m) * 2 + role) * size_t(T - 1) + seg0 + row];
+                  s.sel[(m * 2 + role) * 128 + row] = v;
                 }
             } else {
-              uint32_t d[4] = {255u, 255u, 255u, 255u};
-              if (pt < nseg)
-                counter_draws4(p.seed, uint32_t(p.curve_id0 + n), uint32_t(p.step0 + step), uint32_t(seg0 + pt), 0u,
-                               uint32_t(K), d);
-              for (int q = 0; q < 4; ++q) {
-                const int m = q >> 1;
-                if (m < M) s.sel[(m * 2 + (q & 1)) * WIN_PTS + pt] = uint8_t(d[q]);
+              for (int jp = 0; jp < (M + 1) / 2; ++jp) {
+                uint32_t d[4] = {255u, 255u, 255u, 255u};
+                if (row < nseg)
+                  counter_draws4(p.seed, uint32_t(p.curve_id0 + n), uint32_t(p.step0 + step), uint32_t(seg0 + row),
+                                 uint32_t(jp), uint32_t(K), d);
+                for (int q = 0; q < 4; ++q) {
+                  const int m = 2 * jp + (q >> 1);
+                  if (m < M) s.sel[(m * 2 + (q & 1)) * 128 + row] = uint8_t(d[q]);
+                }
               }
             }
           }
-          for (int i = t512; i < 4 * WIN_PTS; i += EPI_THREADS) s.dzs[i] = make_float2(0.f, 0.f);
-          if (t512 < K) s.cnt[t512] = 0;
+          float dzx = 0.f, dzy = 0.f;
           named_bar(3, EPI_THREADS);
-          // ---- per-decoder row lists ----
-          if (t512 <= nseg) {
-            const int pt = t512;
-            int cand[2 * TC_MAX_M];
-            int nc = 0;
-            for (int m = 0; m < M; ++m) {
-              if (pt < nseg) cand[nc++] = s.sel[(m * 2 + 0) * WIN_PTS + pt];
-              if (pt >= 1) cand[nc++] = s.sel[(m * 2 + 1) * WIN_PTS + pt - 1];
-            }
-            for (int i = 0; i < nc; ++i) {
-              bool dup = false;
-              for (int j = 0; j < i; ++j) dup |= (cand[j] == cand[i]);
-              if (!dup) {
-                const int slot = atomicAdd(&s.cnt[cand[i]], 1);
-                s.rows[cand[i] * WIN_PTS + slot] = uint8_t(pt);
-              }
-            }
-          }
-          named_bar(3, EPI_THREADS);
-          if (t512 == 0) {
-            int ni = 0;
-            for (int k = 0; k < K; ++k)
-              for (int q = 0; q * 128 < s.cnt[k]; ++q) ctl->item[ni++] = uint16_t(k | (q << 8));
-            ctl->nitems = ni;
-            __threadfence_block();
-            mbar_arrive(win_ready);
-          }
-          named_bar(3, EPI_THREADS);
-          const int nitems = ctl->nitems;
-          // small weights (W1, b1, b2, b3) of this group's first item
-          if (chain_id < nitems && tg < 144)
-            cp_async16(swbuf + swsel * 576 + tg * 4, dec_ptr(p.packed, ctl->item[chain_id] & 0xFF) + tg * 4);
+          const float2 z = s.zs[row];
+          const float2 zx2 = make_float2(z.x, z.x), zy2 = make_float2(z.y, z.y);
 
           // =============================== forward ===============================
-          for (int it = chain_id; it < nitems; it += 2) {
-            const int k = ctl->item[it] & 0xFF, q0 = (ctl->item[it] >> 8) * 128;
-            const bool active = q0 + row < s.cnt[k];
-            // tcgen05.ld/st are warp-collective (.sync.aligned): a warp takes part as soon as one of
-            // its 32 rows is in use; unused lanes compute on point 0 and store nothing
-            const bool wact = q0 + (warp & 3) * 32 < s.cnt[k];
-            const int pt = active ? s.rows[k * WIN_PTS + q0 + row] : 0;
+          for (int k = chain_id; k < K; k += 2) {
             // small weights of decoder k were prefetched into swbuf[swsel]; prefetch the next item's
+            PH_T0();
             cp_async_wait_all();
             named_bar(bar_id, GROUP_THREADS);
+            PH_ADD(0);
             const float* sw = swbuf + swsel * 576;
             {
-              int nx = it + 2;
-              if (nx >= nitems) nx = GRAD ? chain_id : -1;
-              if (nx >= 0 && tg < 144)
-                cp_async16(swbuf + (swsel ^ 1) * 576 + tg * 4, dec_ptr(p.packed, ctl->item[nx] & 0xFF) + tg * 4);
+              int kn = k + 2;
+              if (kn >= K) kn = GRAD ? chain_id : (last_tile ? -1 : chain_id);
+              if (kn >= 0 && kn < K && tg < 144)
+                cp_async16(swbuf + (swsel ^ 1) * 576 + tg * 4, dec_ptr(p.packed, kn) + tg * 4);
             }
             swsel ^= 1;
-            const float2 z = s.zs[pt];
-            const float2 zx2 = make_float2(z.x, z.x), zy2 = make_float2(z.y, z.y);
             // layer 1 (CUDA cores, fp32) -> A1 in X[col0 : col0+64]
-            if (wact) {
 #pragma unroll
-              for (int c0 = 0; c0 < 64; c0 += 32) {
-                uint32_t v[32];
+            for (int c0 = 0; c0 < 64; c0 += 32) {
+              uint32_t v[32];
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                  const int c = col0 + c0 + j;
-                  const float4 wx = *reinterpret_cast<const float4*>(sw + OFF_W1X + c);
-                  const float4 wy = *reinterpret_cast<const float4*>(sw + OFF_W1Y + c);
-                  const float4 bb = *reinterpret_cast<const float4*>(sw + OFF_B1 + c);
-                  const float2 h0 = __ffma2_rn(make_float2(wy.x, wy.y), zy2,
-                                               __ffma2_rn(make_float2(wx.x, wx.y), zx2, make_float2(bb.x, bb.y)));
-                  const float2 h1 = __ffma2_rn(make_float2(wy.z, wy.w), zy2,
-                                               __ffma2_rn(make_float2(wx.z, wx.w), zx2, make_float2(bb.z, bb.w)));
-                  v[j] = relu_tf32(h0.x);
-                  v[j + 1] = relu_tf32(h0.y);
-                  v[j + 2] = relu_tf32(h1.x);
-                  v[j + 3] = relu_tf32(h1.y);
-                }
-                tmem_st32(colX + col0 + c0, v);
+              for (int j = 0; j < 32; j += 4) {
+                const int c = col0 + c0 + j;
+                const float4 wx = *reinterpret_cast<const float4*>(sw + OFF_W1X + c);
+                const float4 wy = *reinterpret_cast<const float4*>(sw + OFF_W1Y + c);
+                const float4 bb = *reinterpret_cast<const float4*>(sw + OFF_B1 + c);
+                const float2 h0 = __ffma2_rn(make_float2(wy.x, wy.y), zy2,
+                                             __ffma2_rn(make_float2(wx.x, wx.y), zx2, make_float2(bb.x, bb.y)));
+                const float2 h1 = __ffma2_rn(make_float2(wy.z, wy.w), zy2,
+                                             __ffma2_rn(make_float2(wx.z, wx.w), zx2, make_float2(bb.z, bb.w)));
+                v[j] = relu_tf32(h0.x);
+                v[j + 1] = relu_tf32(h0.y);
+                v[j + 2] = relu_tf32(h1.x);
+                v[j + 3] = relu_tf32(h1.y);
               }
+              tmem_st32(colX + col0 + c0, v);
             }
+            PH_ADD(1);
             tmem_wait_st();
             tc_fence_before();
             mbar_arrive(&a_ready[chain_id]);
+            PH_ADD(2);
             // layer 2 epilogue: D2 (Y) -> relu(+b2) -> A2 (Y, in place), mask bits
             { STAT_T0(); mbar_wait(&acc_ready[chain_id], ph_acc); STAT_ADD(w_acc); }
             ph_acc ^= 1;
             tc_fence_after();
-            if (wact) {
+            PH_ADD(3);
+            {
               uint32_t v0[32], v1[32];
               tmem_ld32x2_sync(colY + col0, colY + col0 + 32, v0, v1);
+              PH_ADD(4);
               uint32_t bits0 = 0, bits1 = 0;
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
@@ -482,66 +433,75 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                 const float4 b1 = *reinterpret_cast<const float4*>(sw + OFF_B2 + col0 + 32 + j);
                 const float2 p0 = __fadd2_rn(make_float2(__uint_as_float(v0[j]), __uint_as_float(v0[j + 1])), make_float2(b0.x, b0.y));
                 const float2 p1 = __fadd2_rn(make_float2(__uint_as_float(v0[j + 2]), __uint_as_float(v0[j + 3])), make_float2(b0.z, b0.w));
-                const float2 q0f = __fadd2_rn(make_float2(__uint_as_float(v1[j]), __uint_as_float(v1[j + 1])), make_float2(b1.x, b1.y));
-                const float2 q1f = __fadd2_rn(make_float2(__uint_as_float(v1[j + 2]), __uint_as_float(v1[j + 3])), make_float2(b1.z, b1.w));
+                const float2 q0 = __fadd2_rn(make_float2(__uint_as_float(v1[j]), __uint_as_float(v1[j + 1])), make_float2(b1.x, b1.y));
+                const float2 q1 = __fadd2_rn(make_float2(__uint_as_float(v1[j + 2]), __uint_as_float(v1[j + 3])), make_float2(b1.z, b1.w));
                 if (p0.x > 0.f) bits0 |= 1u << j;
                 if (p0.y > 0.f) bits0 |= 2u << j;
                 if (p1.x > 0.f) bits0 |= 4u << j;
                 if (p1.y > 0.f) bits0 |= 8u << j;
-                if (q0f.x > 0.f) bits1 |= 1u << j;
-                if (q0f.y > 0.f) bits1 |= 2u << j;
-                if (q1f.x > 0.f) bits1 |= 4u << j;
-                if (q1f.y > 0.f) bits1 |= 8u << j;
+                if (q0.x > 0.f) bits1 |= 1u << j;
+                if (q0.y > 0.f) bits1 |= 2u << j;
+                if (q1.x > 0.f) bits1 |= 4u << j;
+                if (q1.y > 0.f) bits1 |= 8u << j;
                 v0[j] = relu_tf32(p0.x); v0[j + 1] = relu_tf32(p0.y); v0[j + 2] = relu_tf32(p1.x); v0[j + 3] = relu_tf32(p1.y);
-                v1[j] = relu_tf32(q0f.x); v1[j + 1] = relu_tf32(q0f.y); v1[j + 2] = relu_tf32(q1f.x); v1[j + 3] = relu_tf32(q1f.y);
+                v1[j] = relu_tf32(q0.x); v1[j + 1] = relu_tf32(q0.y); v1[j + 2] = relu_tf32(q1.x); v1[j + 3] = relu_tf32(q1.y);
               }
               tmem_st32(colY + col0, v0);
               tmem_st32(colY + col0 + 32, v1);
-              if (GRAD && active) *reinterpret_cast<uint2*>(maskws + (it * 128 + row) * 4 + half * 2) = make_uint2(bits0, bits1);
+              if (GRAD) *reinterpret_cast<uint2*>(maskws + (k * 128 + row) * 4 + half * 2) = make_uint2(bits0, bits1);
             }
+            PH_ADD(5);
             tmem_wait_st();
             tc_fence_before();
             mbar_arrive(&a_ready[chain_id]);
-            // layer 3 epilogue: D3 (X[0:64]) + b3 -> the slots of this point that drew decoder k
+            PH_ADD(6);
+            // layer 3 epilogue: D3 (X[0:64]) + b3 -> XD slots that selected decoder k
             { STAT_T0(); mbar_wait(&acc_ready[chain_id], ph_acc); STAT_ADD(w_acc); }
             ph_acc ^= 1;
             tc_fence_after();
-            if (wact) {
+            PH_ADD(7);
+            {
               uint32_t xv[32];
               tmem_ld32_sync(colX + xc0, xv);
-              float x[32];
+              bool any = false;
+              for (int m = 0; m < M; ++m)
+                any |= (s.sel[(m * 2 + 0) * 128 + row] == k) | (row >= 1 && s.sel[(m * 2 + 1) * 128 + row - 1] == k);
+              if (any) {
+                float x[32];
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 bb = *reinterpret_cast<const float4*>(sw + OFF_B3 + xc0 + j);
-                x[j] = __uint_as_float(xv[j]) + bb.x;
-                x[j + 1] = __uint_as_float(xv[j + 1]) + bb.y;
-                x[j + 2] = __uint_as_float(xv[j + 2]) + bb.z;
-                x[j + 3] = __uint_as_float(xv[j + 3]) + bb.w;
-              }
-              for (int m = 0; m < (active ? M : 0); ++m) {
-                // role 0: this point is the left end of its segment; role 1: right end of the previous one
-                if (s.sel[(m * 2 + 0) * WIN_PTS + pt] == k) {
-                  float4* d = reinterpret_cast<float4*>(s.XD + (m * WIN_PTS + pt) * XD_STRIDE + xc0);
-#pragma unroll
-                  for (int q = 0; q < 8; ++q)
-                    if (q < nq) d[q] = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+                for (int j = 0; j < 32; j += 4) {
+                  const float4 bb = *reinterpret_cast<const float4*>(sw + OFF_B3 + xc0 + j);
+                  x[j] = __uint_as_float(xv[j]) + bb.x;
+                  x[j + 1] = __uint_as_float(xv[j + 1]) + bb.y;
+                  x[j + 2] = __uint_as_float(xv[j + 2]) + bb.z;
+                  x[j + 3] = __uint_as_float(xv[j + 3]) + bb.w;
                 }
-                if (pt >= 1 && s.sel[(m * 2 + 1) * WIN_PTS + pt - 1] == k) {
-                  float4* d = reinterpret_cast<float4*>(X2 + (m * WIN_PTS + pt - 1) * XD_STRIDE + xc0);
+                for (int m = 0; m < M; ++m) {
+                  // role 0: this point is the left end of its segment; role 1: right end of the previous one
+                  if (s.sel[(m * 2 + 0) * 128 + row] == k) {
+                    float4* d = reinterpret_cast<float4*>(s.XD + (m * 128 + row) * XD_STRIDE + xc0);
 #pragma unroll
-                  for (int q = 0; q < 8; ++q)
-                    if (q < nq) d[q] = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+                    for (int q = 0; q < 8; ++q)
+                      if (q < nq) d[q] = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+                  }
+                  if (row >= 1 && s.sel[(m * 2 + 1) * 128 + row - 1] == k) {
+                    float4* d = reinterpret_cast<float4*>(X2 + (m * 128 + row - 1) * XD_STRIDE + xc0);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                      if (q < nq) d[q] = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+                  }
                 }
               }
             }
+            PH_ADD(8);
           }
           named_bar(3, EPI_THREADS);
 
           // ======================= x2 - x1 and the energy =======================
           {
             float e = 0.f, l = 0.f;
-            for (int idx = t512; idx < M * WIN_PTS; idx += EPI_THREADS) {
-              const int r = idx & (WIN_PTS - 1);
+            for (int idx = t512; idx < M * 128; idx += EPI_THREADS) {
+              const int r = idx & 127;
               if (r < nseg) {
                 float4* d0 = reinterpret_cast<float4*>(s.XD + idx * XD_STRIDE);
                 const float4* d1 = reinterpret_cast<const float4*>(X2 + idx * XD_STRIDE);
@@ -559,39 +519,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
             }
             e = warp_sum(e);
             l = warp_sum(l);
-            if (lane == 0) { s.red[160 + ew] = e; s.red[176 + ew] = l; }
+            if (lane == 0) { s.red[80 + ew] = e; s.red[96 + ew] = l; }
           }
           if (GRAD) named_bar(3, EPI_THREADS);  // the differences are read by other threads below
 
           if (GRAD) {
             // =============================== backward ===============================
-            for (int it = chain_id; it < nitems; it += 2) {
-              const int k = ctl->item[it] & 0xFF, q0 = (ctl->item[it] >> 8) * 128;
-              const bool active = q0 + row < s.cnt[k];
-              const bool wact = q0 + (warp & 3) * 32 < s.cnt[k];
-              const int pt = active ? s.rows[k * WIN_PTS + q0 + row] : 0;
+            for (int k = chain_id; k < K; k += 2) {
+              PH_T0();
               cp_async_wait_all();
               named_bar(bar_id, GROUP_THREADS);
+              PH_ADD(10);
               const float* sw = swbuf + swsel * 576;
               {
-                const int nx = it + 2;
-                if (nx < nitems && tg < 144)
-                  cp_async16(swbuf + (swsel ^ 1) * 576 + tg * 4, dec_ptr(p.packed, ctl->item[nx] & 0xFF) + tg * 4);
+                int kn = k + 2;
+                if (kn >= K) kn = last_tile ? -1 : chain_id;
+                if (kn >= 0 && kn < K && tg < 144)
+                  cp_async16(swbuf + (swsel ^ 1) * 576 + tg * 4, dec_ptr(p.packed, kn) + tg * 4);
               }
               swsel ^= 1;
-              const float2 z = s.zs[pt];
-              const float2 zx2 = make_float2(z.x, z.x), zy2 = make_float2(z.y, z.y);
               // mask words for E-B3 (L2 round trip overlaps the G build and the first MMA)
-              uint2 bits = make_uint2(0u, 0u);
-              if (active) bits = *reinterpret_cast<const uint2*>(maskws + (it * 128 + row) * 4 + half * 2);
+              const uint2 bits = *reinterpret_cast<const uint2*>(maskws + (k * 128 + row) * 4 + half * 2);
               // G = dE/dx_k (this point), columns xc0 .. xc0+31 -> X[xc0 : xc0+32]
-              if (wact) {
+              {
                 float g[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) g[j] = 0.f;
-                for (int m = 0; m < (active ? M : 0); ++m) {
-                  if (pt >= 1 && s.sel[(m * 2 + 1) * WIN_PTS + pt - 1] == k) {
-                    const float4* d = reinterpret_cast<const float4*>(s.XD + (m * WIN_PTS + pt - 1) * XD_STRIDE + xc0);
+                for (int m = 0; m < M; ++m) {
+                  if (row >= 1 && s.sel[(m * 2 + 1) * 128 + row - 1] == k) {
+                    const float4* d = reinterpret_cast<const float4*>(s.XD + (m * 128 + row - 1) * XD_STRIDE + xc0);
 #pragma unroll
                     for (int q = 0; q < 8; ++q)
                       if (q < nq) {
@@ -599,8 +555,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                         g[4 * q] += v.x; g[4 * q + 1] += v.y; g[4 * q + 2] += v.z; g[4 * q + 3] += v.w;
                       }
                   }
-                  if (s.sel[(m * 2 + 0) * WIN_PTS + pt] == k) {
-                    const float4* d = reinterpret_cast<const float4*>(s.XD + (m * WIN_PTS + pt) * XD_STRIDE + xc0);
+                  if (s.sel[(m * 2 + 0) * 128 + row] == k) {
+                    const float4* d = reinterpret_cast<const float4*>(s.XD + (m * 128 + row) * XD_STRIDE + xc0);
 #pragma unroll
                     for (int q = 0; q < 8; ++q)
                       if (q < nq) {
@@ -614,14 +570,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                 for (int j = 0; j < 32; ++j) v[j] = tf32_round_bits(__float_as_uint(coefm * g[j]));
                 tmem_st32(colX + xc0, v);
               }
+              PH_ADD(11);
               tmem_wait_st();
               tc_fence_before();
               mbar_arrive(&a_ready[chain_id]);
+              PH_ADD(12);
               // dh2 = (G W3) * mask2 -> A4 (Y, in place)
               { STAT_T0(); mbar_wait(&acc_ready[chain_id], ph_acc); STAT_ADD(w_acc); }
               ph_acc ^= 1;
               tc_fence_after();
-              if (wact) {
+              PH_ADD(13);
+              {
                 uint32_t v0[32], v1[32];
                 tmem_ld32x2_sync(colY + col0, colY + col0 + 32, v0, v1);
 #pragma unroll
@@ -632,14 +591,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                 tmem_st32(colY + col0, v0);
                 tmem_st32(colY + col0 + 32, v1);
               }
+              PH_ADD(14);
               tmem_wait_st();
               tc_fence_before();
               mbar_arrive(&a_ready[chain_id]);
-              // dh1 = (dh2 W2) * mask1 (recomputed); dz[point] += dh1 W1 over this thread's 64 hidden units
+              PH_ADD(15);
+              // dh1 = (dh2 W2) * mask1 (recomputed); dz += dh1 W1 over this thread's 64 hidden units
               { STAT_T0(); mbar_wait(&acc_ready[chain_id], ph_acc); STAT_ADD(w_acc); }
               ph_acc ^= 1;
               tc_fence_after();
-              if (wact) {
+              PH_ADD(16);
+              {
                 uint32_t v0[32], v1[32];
                 tmem_ld32x2_sync(colX + col0, colX + col0 + 32, v0, v1);
                 float2 ax = make_float2(0.f, 0.f), ay = make_float2(0.f, 0.f);
@@ -656,46 +618,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                   ax = __ffma2_rn(dh, wx, ax);
                   ay = __ffma2_rn(dh, wy, ay);
                 }
-                // a point occurs at most once per item and the items of a chain run in order:
-                // plain read-modify-write, deterministic
-                if (active) {
-                  float2* dzp = &s.dzs[(chain_id * 2 + half) * WIN_PTS + pt];
-                  float2 acc = *dzp;
-                  acc.x += ax.x + ax.y;
-                  acc.y += ay.x + ay.y;
-                  *dzp = acc;
-                }
+                dzx += ax.x + ax.y;
+                dzy += ay.x + ay.y;
               }
+              PH_ADD(17);
             }
+            s.dzs[(chain_id * 2 + half) * 128 + row] = make_float2(dzx, dzy);
           }
           named_bar(3, EPI_THREADS);
-          // ---- d(omega) += P^T dz over the points of the window, energy partials ----
-          if (GRAD && t512 < WIN_PTS) {
-            const int pt = t512;
+          // ---- d(omega) += P^T dz, energy partials ----
+          if (GRAD && chain_id == 0 && half == 0) {
             float P[MAX_KB];
-            design_row(p.t[min(seg0 + pt, T - 1)], n_poly, Kb, s.basis, P);
-            const float2 d0 = s.dzs[pt], d1 = s.dzs[WIN_PTS + pt], d2 = s.dzs[2 * WIN_PTS + pt], d3 = s.dzs[3 * WIN_PTS + pt];
+            design_row(s.ts[row], n_poly, Kb, s.basis, P);
+            const float2 d0 = s.dzs[row], d1 = s.dzs[128 + row], d2 = s.dzs[256 + row], d3 = s.dzs[384 + row];
             const float dx = (d0.x + d1.x) + (d2.x + d3.x), dy = (d0.y + d1.y) + (d2.y + d3.y);
 #pragma unroll
             for (int k = 0; k < MAX_KB; ++k)
               if (k < Kb) {
                 const float cx = warp_sum(P[k] * dx), cy = warp_sum(P[k] * dy);
-                if (lane == 0) { s.red[ew * 20 + 2 * k] = cx; s.red[ew * 20 + 2 * k + 1] = cy; }
+                if (lane == 0) { s.red[(warp & 3) * 20 + 2 * k] = cx; s.red[(warp & 3) * 20 + 2 * k + 1] = cy; }
               }
           }
           if (t512 == 0) {
             float ee = 0.f, ll = 0.f;
-            for (int w = 0; w < 16; ++w) { ee += s.red[160 + w]; ll += s.red[176 + w]; }
+            for (int w = 0; w < 16; ++w) { ee += s.red[80 + w]; ll += s.red[96 + w]; }
             e_tot += ee;
             l_tot += ll;
           }
           named_bar(3, EPI_THREADS);
-          if (GRAD && t512 < 2 * Kb) {
-            float g = 0.f;
-            for (int w = 0; w < 8; ++w) g += s.red[w * 20 + t512];
-            s.gacc[t512] += g;
-          }
-        }  // windows
+          if (GRAD && t512 < 2 * Kb)
+            s.gacc[t512] += (s.red[t512] + s.red[20 + t512]) + (s.red[40 + t512] + s.red[60 + t512]);
+        }  // tiles
 
         named_bar(3, EPI_THREADS);
         if (t512 == 0) {
@@ -733,7 +686,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
     }  // curves
     cp_async_wait_all();
 #ifdef VLG_TC_STATS
-    if (tg == 0 && blockIdx.x < 1024) g_tc_stats[blockIdx.x * 8 + 4 + chain_id * 2] = w_acc;
+    if (tg == 0 && blockIdx.x < 1024) {
+      g_tc_stats[blockIdx.x * 8 + 4 + chain_id * 2] = w_acc;
+      if (chain_id == 0) for (int i = 0; i < 24; ++i) g_tc_phase[blockIdx.x * 24 + i] = ph_t[i];
+    }
 #endif
     (void)w_acc;
   }
@@ -754,24 +710,26 @@ static int tc_grid(int N) {
   return N < sms ? N : sms;
 }
 
-// per CTA: layer-2 ReLU mask bits [K+8 items][128 rows][4 words] + right-end outputs x2 [M][256][52] fp32
+// per CTA: layer-2 ReLU mask bits [K][128 rows][4 words] + right-end outputs x2 [M][128][52] fp32
 size_t tc_workspace_bytes(int N, int, int K, int M) {
-  return size_t(tc_grid(N)) * (size_t(K + 8) * 2048 + size_t(M) * WIN_PTS * XD_STRIDE * 4);
+  return size_t(tc_grid(N)) * (size_t(K) * 2048 + size_t(M) * 128 * XD_STRIDE * 4);
 }
 
 #ifdef VLG_TC_STATS
 extern "C" int vlg_debug_tc_stats(long long* host_out, int n) {
   return cudaMemcpyFromSymbol(host_out, g_tc_stats, size_t(n) * 8 * sizeof(long long)) == cudaSuccess ? 0 : -3;
 }
+extern "C" int vlg_debug_tc_phase(long long* host_out, int n) {
+  return cudaMemcpyFromSymbol(host_out, g_tc_phase, size_t(n) * 24 * sizeof(long long)) == cudaSuccess ? 0 : -3;
+}
 #endif
 
 cudaError_t launch_tc(const StepParams& p, bool grad, cudaStream_t stream) {
   if (p.precision != 1) return cudaErrorNotSupported;  // 3xTF32 not built yet
-  if (p.M > TC_MAX_M || p.K > TC_MAX_K) return cudaErrorNotSupported;
-  const int nst = tc_stages(p.M, p.K);
+  const int nst = tc_stages(p.M);
   if (nst < 2) return cudaErrorNotSupported;
   if (p.workspace == nullptr || p.workspace_bytes < tc_workspace_bytes(p.N, p.T, p.K, p.M)) return cudaErrorInvalidValue;
-  const size_t smem = tc_smem_fixed_bytes(p.M, p.K) + size_t(2) * nst * STAGE_BYTES;
+  const size_t smem = tc_smem_fixed_bytes(p.M) + size_t(2) * nst * STAGE_BYTES;
   const int grid = tc_grid(p.N);
   cudaError_t e;
   if (grad) {
