@@ -67,9 +67,8 @@ def synthetic_workload(n_curves, seed=0):
 
 
 def shard_range(n, rank, world):
-    per = (n + world - 1) // world
-    lo = min(rank * per, n)
-    return lo, min(lo + per, n)
+    from vlg_b200.sharding import shard_range as sr
+    return sr(n, rank, world)
 
 
 class ClockSampler:

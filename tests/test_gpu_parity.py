@@ -289,3 +289,57 @@ def test_final_length_after_150_steps(vlg, prec, tol):
     print(f"final-length rel err after {S} steps: {prec} kernel {ours:.2e}; reference fp32 vs fp64 {gap_ref32:.2e}")
     assert ours < tol
     assert np.abs(np.sqrt(trace / ref) - 1).max() < tol * 2
+
+
+@pytest.mark.parametrize("T,N,K,M,n_poly", [(2, 1, 1, 1, 1), (3, 2, 2, 2, 2), (128, 3, 3, 2, 4), (255, 2, 5, 1, 8),
+                                           (256, 1, 16, 2, 4), (257, 2, 4, 2, 4), (600, 3, 1, 1, 4), (513, 150, 7, 2, 4)])
+def test_tf32_edge_shapes_against_fp32_kernel(vlg, T, N, K, M, n_poly):
+    """Window boundaries (255/256/257 points), a decoder drawn by more than 128 points of a window
+    (K=1: two 128-row items per window), a single segment, more curves than SMs (persistent CTAs
+    walk several curves), K up to 16.  Compared against the fp32 kernel on identical draws."""
+    rng = np.random.default_rng(T * 131 + K)
+    W = dict(W1=rng.normal(size=(K, 128, 2)) * 0.7, b1=rng.normal(size=(K, 128)) * 0.3,
+             W2=rng.normal(size=(K, 128, 128)) * 0.09, b2=rng.normal(size=(K, 128)) * 0.1,
+             W3=rng.normal(size=(K, 50, 128)) * 0.09, b3=rng.normal(size=(K, 50)) * 0.1)
+    W = {k: v.astype(np.float32) for k, v in W.items()}
+    basis, _ = vlg.construct_nullspace_basis(n_poly)
+    g = dict(a=rng.uniform(-3, 3, (N, 2)).astype(np.float32), b=rng.uniform(-3, 3, (N, 2)).astype(np.float32),
+             omega_init=(0.1 * rng.normal(size=(N, n_poly + 1, 2))).astype(np.float32), basis=basis.numpy(),
+             n_poly=n_poly, **W)
+    S = 2
+    dec = make_decoders(vlg, g, K)
+    t = torch.linspace(0, 1, T, device="cuda")
+    res = {}
+    for prec in ("fp32", "tf32"):
+        model = make_model(vlg, g)
+        _, trace = vlg.optimize_splines(model, dec, t, S, M=M, seed=11, curve_id0=5, precision=prec, return_trace=True)
+        e, ln = vlg.compute_energy_mc(model, dec, t, M=M, seed=11, step=S, curve_id0=5, precision=prec,
+                                      return_length=True)
+        res[prec] = (trace.cpu().numpy(), model.omega.cpu().numpy(), e.cpu().numpy(), ln.cpu().numpy())
+    # with random weights and few decoders the energies are single-decoder-like (differences of nearby
+    # outputs), where TF32 is at its worst: allow 2e-2 on energies here; the real-checkpoint cases above
+    # carry the 1e-3 length bound
+    # K = 1 is the single-decoder energy (sum of tiny differences of large outputs): TF32 is known to be
+    # inadequate there (SURVEY hard part 1: ~13 % mean error) -- that path is served by the fp32 kernel;
+    # here it only has to be structurally right (same order of magnitude)
+    tol = 0.5 if K == 1 else 2e-2
+    assert np.abs(res["tf32"][0] / res["fp32"][0] - 1).max() < tol
+    assert np.abs(res["tf32"][2] / res["fp32"][2] - 1).max() < tol
+    assert np.abs(res["tf32"][3] / res["fp32"][3] - 1).max() < tol
+    assert np.abs(res["tf32"][1] - res["fp32"][1]).max() < 0.25 * S * 1e-3 + 1e-6
+
+
+def test_tf32_is_deterministic_and_shard_independent(vlg):
+    g = Hh.load("ens_seed12_entropy")
+    dec = make_decoders(vlg, g, 10)
+    t = torch.linspace(0, 1, 2000, device="cuda")
+    outs = []
+    for _ in range(2):
+        m = make_model(vlg, g)
+        e = vlg.optimize_splines(m, dec, t, 2, M=2, seed=5, curve_id0=40, precision="tf32")
+        outs.append((m.omega.clone(), e.clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    sub = {k: (v[2:5] if k in ("a", "b", "omega_init") else v) for k, v in g.items()}
+    m = make_model(vlg, sub)
+    e = vlg.optimize_splines(m, dec, t, 2, M=2, seed=5, curve_id0=42, precision="tf32")
+    assert torch.equal(m.omega, outs[0][0][2:5]) and torch.equal(e, outs[0][1][2:5])
