@@ -287,6 +287,12 @@ def run_gpu_arm(args):
         # roofline of the step kernel on THIS rank: algorithmic FLOPs / kernel time
         flops_local = n_local * args.steps * T_POINTS * K_DEC * FLOP_PER_POINT_DECODER
         achieved = flops_local / (kernel_ms * 1e-3) / 1e12
+        traffic = None
+        tf = ROOT / "profiles" / "r01_traffic.json"
+        if tf.exists() and args.precision == "tf32":
+            # DRAM bytes per launch, scaled from the committed ncu capture of the same kernel
+            per = json.loads(tf.read_text())["dram_bytes_per_spline_step"]
+            traffic = per * n_local * args.steps / max(1, len(kernel_events))
         line = {
             "metric": METRIC, "value": value, "unit": "spline-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
@@ -300,7 +306,7 @@ def run_gpu_arm(args):
                     "d2h_bytes_per_step": d2h * len(kernel_events) / args.steps},
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "kernel": "tc_curve_kernel<true>" if args.precision == "tf32" else "simt_curve_kernel<true>",
                          "flop_per_spline_step": T_POINTS * K_DEC * FLOP_PER_POINT_DECODER,
                          "kernel_ms_per_step": kernel_ms / args.steps},
