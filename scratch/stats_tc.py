@@ -24,15 +24,3 @@ for i, nm in enumerate(names):
     if nm != "-":
         print(f"{nm:22s} mean {st[:, i].mean():12.0f} cycles  ({100 * st[:, i].mean() / st[:, 3].mean():5.1f}% of mma total)")
 
-ph = (ctypes.c_longlong * (nc * 24))()
-lib.vlg_debug_tc_phase.argtypes = [ctypes.c_void_p, ctypes.c_int]
-assert lib.vlg_debug_tc_phase(ph, nc) == 0
-ph = np.array(ph).reshape(nc, 24).astype(np.float64).mean(0)
-items = 16 * 5 * 3  # items of chain 0 over the 3 launches (2 warm-up + 1)
-names = {0: "F sw wait+bar", 1: "F1 compute+st", 2: "F1 wait_st+arrive", 3: "wait acc F2", 4: "E-F2 tmem ld", 5: "E-F2 compute+st",
-         6: "E-F2 wait_st+arrive", 7: "wait acc F3", 8: "E-F3 ld+store", 10: "B sw wait+bar", 11: "G build+st", 12: "G wait_st+arrive",
-         13: "wait acc B3", 14: "E-B3 ld+mask+st", 15: "E-B3 wait_st+arrive", 16: "wait acc B2", 17: "E-B2 ld+dz"}
-tot = 0
-for i, nm in names.items():
-    print(f"phase {nm:22s} {ph[i] / items:8.0f} cycles per item"); tot += ph[i] / items
-print("item total (fwd+bwd)", tot)

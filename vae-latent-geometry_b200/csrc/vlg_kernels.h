@@ -11,6 +11,7 @@ struct StepParams {
   int K, X;                    // active decoders, output width
   int N, T, n_poly, Kb, M;
   int steps, step0;
+  int unit_steps;              // Adam steps per work unit (set by the tensor-core launcher)
   const float* a;
   const float* b;
   float* omega;

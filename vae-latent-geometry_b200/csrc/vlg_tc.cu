@@ -1,7 +1,8 @@
 // tcgen05 (TF32) geodesic step kernel -- the tensor-core variant (<=1e-3 relative on lengths).
 //
-// Persistent CTAs (one per SM, 608 threads), each walking a strided list of curves; per curve
-// all `steps` Adam steps run inside the kernel.  The two 128-wide decoder layers and their
+// Persistent CTAs (one per SM, 608 threads) pull work units -- (curve, chunk of Adam steps) -- from
+// a global queue; a curve's chunks are chained through its omega/m/v in HBM, so a launch of
+// `steps` steps has no tail longer than one chunk.  The two 128-wide decoder layers and their
 // transposes run as tcgen05.mma kind::tf32 with
 //   * M = 128 rows = the 128 TMEM lanes,
 //   * the A operand (activations) living in TENSOR MEMORY: the epilogue threads write the
@@ -13,7 +14,8 @@
 // ROW COMPACTION.  The MC energy touches, per curve point, only the decoders drawn for the two
 // segments that meet there (<= 2M of K; 3.4 of 10 on average), and the reference's dense
 // K x T forward/backward spends two thirds of its FLOPs on outputs that are multiplied by zero.
-// Here a curve is cut into windows of 256 points (255 segments); for every decoder the points
+// Here a curve is cut into windows of W points (W chosen on the host so that a decoder is drawn by
+// ~115 points of a window on average; W-1 segments); for every decoder the points
 // of the window that drew it are gathered into the rows of one 128-row MMA tile ("item"; a
 // decoder drawn by more than 128 points simply gets several items).  Results are identical:
 // each selected (point, decoder) pair goes through exactly the same arithmetic.
@@ -31,6 +33,8 @@
 // right-end output x2 in an L2-resident workspace) -> one pass forms x2-x1 and the energy ->
 // backward items (input gradient only; layer-2 ReLU masks as bits in the workspace, layer-1
 // mask recomputed) -> dz per point -> d(omega).  Penalty gradient and Adam as in vlg_simt.cu.
+#include <stdlib.h>
+
 #include "vlg_common.cuh"
 #include "vlg_kernels.h"
 #include "vlg_tcgen05.cuh"
@@ -58,11 +62,10 @@ constexpr int FIRST_EPI_WARP = 3;
 constexpr int STAGE_BYTES = 16384;
 constexpr int MAX_STAGES = 4;         // per chain
 constexpr int XD_STRIDE = 52;         // floats per stored decoder output row (X <= 52; 16 B rows)
-constexpr int WIN_PTS = 256;          // curve points per window
-constexpr int WIN_SEGS = 255;         // segments per window: neighbouring windows share one point
-constexpr int TC_MAX_M = 2;           // MC samples supported by this kernel (shared-memory budget)
+constexpr int TC_MAX_W = 512;         // curve points per window (runtime W <= this); neighbouring windows share one point
+constexpr int TC_MAX_M = 2;           // MC samples supported by this kernel
 constexpr int TC_MAX_K = 64;          // decoders
-constexpr int MAX_ITEMS = TC_MAX_K + 8;  // sum_k ceil(n_k/128) <= K + 4*256/128
+constexpr int MAX_ITEMS = TC_MAX_K + 16;  // sum_k ceil(n_k/128) <= K + 2*M*W/128
 
 // the four tensor-core GEMMs of one decoder
 struct OpInfo {
@@ -108,6 +111,9 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 
+// work-queue header at the start of the workspace: 64 words + one progress word per curve, 256 B aligned
+__host__ __device__ inline size_t tc_queue_words(int N) { return (size_t(64 + N) + 63) / 64 * 64; }
+
 struct WinCtl {
   int nitems;
   int pad;
@@ -116,78 +122,81 @@ struct WinCtl {
 
 struct TcSmem {
   unsigned char* ring;  // [chain][stage] 16 KB
-  float* XD;            // [m][256][52]: left-end outputs x1, then (after the energy pass) x2 - x1
-  uint8_t* sel;         // [m][role][256] drawn decoder per segment
-  uint8_t* rows;        // [K][256] points of the window that drew decoder k
+  float* XD;            // [m][W][52]: left-end outputs x1, then (after the energy pass) x2 - x1
+  uint8_t* sel;         // [m][role][W] drawn decoder per segment
+  uint16_t* rows;       // [K][W] points of the window that drew decoder k
   int* cnt;             // [K]
   WinCtl* ctl;          // [2] item lists, double buffered by window parity
   float* sw;            // [chain][buf] 576 floats
-  float2* zs;           // 256 latent points of the window
-  float2* dzs;          // [chain][half][256]
+  float2* zs;           // W latent points of the window
+  float2* dzs;          // [chain][half][W]
   float* coef;          // 64
   float* basis;         // 288
   float* om;            // 56
   float* gacc;          // 20
-  float* red;           // 8*20 + 32
+  float* red;           // 16*20 + 32
   uint64_t* bars;       // full[2][MAX_STAGES], empty[2][MAX_STAGES], a_ready[2], acc_ready[2], win_ready
-  uint32_t* tmem_base;
+  uint32_t* tmem_base;  // [0] TMEM base address, [1] current work unit
 };
 
 constexpr int CTL_FLOATS = (2 * sizeof(WinCtl) + 3) / 4;
 constexpr int BAR_WORDS = 2 * (4 * MAX_STAGES + 5);
 
-__device__ __forceinline__ TcSmem tc_carve(unsigned char* base, int M, int K, int nst) {
+__device__ __forceinline__ TcSmem tc_carve(unsigned char* base, int W, int K, int M, int nst) {
   TcSmem s;
   s.ring = base;
   float* f = reinterpret_cast<float*>(base + 2 * nst * STAGE_BYTES);
-  s.XD = f; f += M * WIN_PTS * XD_STRIDE;
+  s.XD = f; f += M * W * XD_STRIDE;
   s.sw = f; f += 4 * 576;
-  s.zs = reinterpret_cast<float2*>(f); f += 2 * WIN_PTS;
-  s.dzs = reinterpret_cast<float2*>(f); f += 2 * 4 * WIN_PTS;
+  s.zs = reinterpret_cast<float2*>(f); f += 2 * W;
+  s.dzs = reinterpret_cast<float2*>(f); f += 2 * 4 * W;
   s.coef = f; f += 64;
   s.basis = f; f += 4 * MAX_NPOLY * MAX_KB;
   s.om = f; f += 3 * 2 * MAX_KB + 2;
   s.gacc = f; f += 2 * MAX_KB + 2;
-  s.red = f; f += 192;
+  s.red = f; f += 352;
   s.bars = reinterpret_cast<uint64_t*>(f); f += BAR_WORDS;
   s.tmem_base = reinterpret_cast<uint32_t*>(f); f += 4;
   s.ctl = reinterpret_cast<WinCtl*>(f); f += CTL_FLOATS;
   s.cnt = reinterpret_cast<int*>(f); f += TC_MAX_K;
-  s.sel = reinterpret_cast<uint8_t*>(f); f += TC_MAX_M * 2 * WIN_PTS / 4;
-  s.rows = reinterpret_cast<uint8_t*>(f);
+  s.sel = reinterpret_cast<uint8_t*>(f); f += TC_MAX_M * 2 * W / 4;
+  s.rows = reinterpret_cast<uint16_t*>(f);
   (void)K;
   return s;
 }
 
 }  // namespace
 
-static size_t tc_smem_fixed_bytes(int M, int K) {
-  size_t fl = size_t(M) * WIN_PTS * XD_STRIDE + 4 * 576 + 2 * WIN_PTS + 2 * 4 * WIN_PTS + 64 + 4 * MAX_NPOLY * MAX_KB +
-              (3 * 2 * MAX_KB + 2) + (2 * MAX_KB + 2) + 192 + BAR_WORDS + 4 + CTL_FLOATS + TC_MAX_K +
-              TC_MAX_M * 2 * WIN_PTS / 4;
-  return fl * 4 + size_t(K) * WIN_PTS;
+static size_t tc_smem_fixed_bytes(int W, int K, int M) {
+  size_t fl = size_t(M) * W * XD_STRIDE + 4 * 576 + 2 * size_t(W) + 2 * 4 * size_t(W) + 64 + 4 * MAX_NPOLY * MAX_KB + (3 * 2 * MAX_KB + 2) +
+              (2 * MAX_KB + 2) + 352 + BAR_WORDS + 4 + CTL_FLOATS + TC_MAX_K + TC_MAX_M * 2 * size_t(W) / 4;
+  return fl * 4 + size_t(K) * W * 2;
 }
-static int tc_stages(int M, int K) {
-  const long budget = 232448 - long(tc_smem_fixed_bytes(M, K));
+static int tc_stages(int W, int K, int M) {
+  const long budget = 232448 - long(tc_smem_fixed_bytes(W, K, M));
   long nst = budget / (2 * STAGE_BYTES);
   if (nst > MAX_STAGES) nst = MAX_STAGES;
   return int(nst);
 }
 
 template <bool GRAD>
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, int nst) {
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, int nst, int W) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int M = p.M, K = p.K, T = p.T, n_poly = p.n_poly, Kb = p.Kb;
-  TcSmem s = tc_carve(smem_raw, M, K, nst);
+  TcSmem s = tc_carve(smem_raw, W, K, M, nst);
+  const int WSEG = W - 1;  // segments per window
   uint64_t* full = s.bars;                       // [2][MAX_STAGES]
   uint64_t* empty = s.bars + 2 * MAX_STAGES;     // [2][MAX_STAGES]
   uint64_t* a_ready = s.bars + 4 * MAX_STAGES;
   uint64_t* acc_ready = s.bars + 4 * MAX_STAGES + 2;
   uint64_t* win_ready = s.bars + 4 * MAX_STAGES + 4;
-  const int nwin = (T - 1 + WIN_SEGS - 1) / WIN_SEGS;
-  const int ncurves = (p.N - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);  // curves of this CTA
-  const long total_win = long(ncurves) * p.steps * nwin;
+  const int nwin = (T - 1 + WSEG - 1) / WSEG;
+  // work queue (zeroed by the host before the launch): [0] next unit, [64 + n] chunks done of curve n
+  unsigned int* queue = reinterpret_cast<unsigned int*>(p.workspace);
+  const int unit_steps = p.unit_steps;
+  const int nchunks = (p.steps + unit_steps - 1) / unit_steps;
+  const unsigned int total_units = unsigned(p.N) * unsigned(nchunks);
 
   if (tid == 0) {
     for (int i = 0; i < 2 * MAX_STAGES; ++i) {
@@ -220,10 +229,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
       unsigned char* ringc = s.ring + c * nst * STAGE_BYTES;
       int slot = 0;
       uint32_t ph = 0;
-      for (long w = 0; w < total_win; ++w) {
+      for (long w = 0;; ++w) {
         mbar_wait(win_ready, uint32_t(w & 1));
         const WinCtl* ctl = &s.ctl[w & 1];
         const int nit = ctl->nitems;
+        if (nit < 0) break;  // no more work units
         for (int phase = 0; phase < (GRAD ? 2 : 1); ++phase)
           for (int i = c; i < nit; i += 2) {
             const int k = ctl->item[i] & 0xFF;
@@ -246,16 +256,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
       int slot[2] = {0, 0}, opi[2] = {0, 0}, nitc[2] = {0, 0};
       int ops_left[2] = {0, 0};      // ops of the chain's current window still to issue
       long win[2] = {0, 0};          // next window whose item list the chain has to pick up
+      bool fin[2] = {false, false};
       uint32_t ph[2] = {0, 0}, ph_a[2] = {0, 0};
       long long w_full = 0, w_issue = 0;
       STAT_T0();
-      while (win[0] < total_win || ops_left[0] > 0 || win[1] < total_win || ops_left[1] > 0) {
+      while (!(fin[0] && fin[1])) {
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
+          if (fin[c]) continue;
           if (ops_left[c] == 0) {
-            if (win[c] >= total_win) continue;
             if (!mbar_test(win_ready, uint32_t(win[c] & 1))) continue;
             const int nit = s.ctl[win[c] & 1].nitems;
+            if (nit < 0) { fin[c] = true; continue; }
             nitc[c] = (nit - c + 1) / 2;  // items of this chain in the window
             ops_left[c] = nitc[c] * (GRAD ? 4 : 2);
             opi[c] = 0;
@@ -326,27 +338,50 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
     const float coefm = 2.0f / float(M);
     long long w_acc = 0;
     long wcount = 0;                            // windows processed by this CTA so far
-    // this CTA's slice of the L2-resident workspace: layer-2 ReLU masks [item][row][4 words], then
-    // the right-end decoder outputs x2 [m][256][52]
-    const size_t ws_cta = size_t(K + 8) * 512 + size_t(M) * WIN_PTS * XD_STRIDE;  // 32-bit words per CTA
-    uint32_t* maskws = reinterpret_cast<uint32_t*>(p.workspace) + size_t(blockIdx.x) * ws_cta;
-    float* X2 = reinterpret_cast<float*>(maskws + size_t(K + 8) * 512);
+    // this CTA's slice of the L2-resident workspace: layer-2 ReLU masks [item][row][4 words], then the
+    // right-end decoder outputs x2 [m][W][52].  (The left-end outputs x1 / the differences stay in shared
+    // memory: with them in L2 too the dE/dx build sits on L2 latency and the kernel runs 2x slower.)
+    const size_t ws_cta = size_t(K + 16) * 512 + size_t(M) * W * XD_STRIDE;  // 32-bit words per CTA
+    uint32_t* maskws = reinterpret_cast<uint32_t*>(p.workspace) + tc_queue_words(p.N) + size_t(blockIdx.x) * ws_cta;
+    float* X1 = s.XD;
+    float* X2 = reinterpret_cast<float*>(maskws + size_t(K + 16) * 512);
 
     for (int i = t512; i < 4 * n_poly * Kb; i += EPI_THREADS) s.basis[i] = p.basis[i];
 
-    for (int n = blockIdx.x; n < p.N; n += gridDim.x) {
+    for (;;) {
+      // ---- next work unit: (curve n, steps [step_lo, step_hi)) ----
+      if (t512 == 0) {
+        const unsigned int u = atomicAdd(&queue[0], 1u);
+        s.tmem_base[1] = u;
+        if (u < total_units && u >= unsigned(p.N)) {
+          // a later chunk of a curve: wait until its previous chunk has been written back
+          const unsigned int* flag = &queue[64 + u % unsigned(p.N)];
+          const unsigned int need = u / unsigned(p.N);
+          unsigned int have;
+          do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(have) : "l"(flag) : "memory");
+            if (have < need) __nanosleep(100);
+          } while (have < need);
+        }
+      }
+      named_bar(3, EPI_THREADS);
+      const unsigned int unit = s.tmem_base[1];
+      if (unit >= total_units) break;
+      const int n = int(unit % unsigned(p.N));
+      const int chunk = int(unit / unsigned(p.N));
+      const int step_lo = chunk * unit_steps, step_hi = min(p.steps, step_lo + unit_steps);
       if (t512 < 2 * Kb) {
-        s.om[t512] = p.omega[size_t(n) * 2 * Kb + t512];
+        s.om[t512] = __ldcg(p.omega + size_t(n) * 2 * Kb + t512);
         if (GRAD) {
-          s.om[2 * MAX_KB + t512] = p.adam_m[size_t(n) * 2 * Kb + t512];
-          s.om[4 * MAX_KB + t512] = p.adam_v[size_t(n) * 2 * Kb + t512];
+          s.om[2 * MAX_KB + t512] = __ldcg(p.adam_m + size_t(n) * 2 * Kb + t512);
+          s.om[4 * MAX_KB + t512] = __ldcg(p.adam_v + size_t(n) * 2 * Kb + t512);
         }
       }
       const float2 pa = make_float2(p.a[2 * n], p.a[2 * n + 1]);
       const float2 pb = make_float2(p.b[2 * n], p.b[2 * n + 1]);
       named_bar(3, EPI_THREADS);
 
-      for (int step = 0; step < p.steps; ++step) {
+      for (int step = step_lo; step < step_hi; ++step) {
         if (t512 < 8 * n_poly) {
           const int r = t512 >> 1, d = t512 & 1;
           float acc = 0.f;
@@ -358,11 +393,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
         named_bar(3, EPI_THREADS);
 
         for (int win = 0; win < nwin; ++win, ++wcount) {
-          const int seg0 = win * WIN_SEGS;
-          const int nseg = min(WIN_SEGS, T - 1 - seg0);
+          const int seg0 = win * WSEG;
+          const int nseg = min(WSEG, T - 1 - seg0);
           WinCtl* ctl = &s.ctl[wcount & 1];
           // ---- window setup: points, draws, accumulators ----
-          if (t512 < WIN_PTS) {
+          if (t512 < W) {
             const int pt = t512;
             const int ti = min(seg0 + pt, T - 1);
             s.zs[pt] = spline_point(p.t[ti], n_poly, s.coef, pa, pb);
@@ -372,7 +407,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                   uint8_t v = 255;
                   if (pt < nseg)
                     v = p.draws[(((size_t(n) * p.steps + step) * M + m) * 2 + role) * size_t(T - 1) + seg0 + pt];
-                  s.sel[(m * 2 + role) * WIN_PTS + pt] = v;
+                  s.sel[(m * 2 + role) * W + pt] = v;
                 }
             } else {
               uint32_t d[4] = {255u, 255u, 255u, 255u};
@@ -381,11 +416,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                                uint32_t(K), d);
               for (int q = 0; q < 4; ++q) {
                 const int m = q >> 1;
-                if (m < M) s.sel[(m * 2 + (q & 1)) * WIN_PTS + pt] = uint8_t(d[q]);
+                if (m < M) s.sel[(m * 2 + (q & 1)) * W + pt] = uint8_t(d[q]);
               }
             }
           }
-          for (int i = t512; i < 4 * WIN_PTS; i += EPI_THREADS) s.dzs[i] = make_float2(0.f, 0.f);
+          for (int i = t512; i < 4 * W; i += EPI_THREADS) s.dzs[i] = make_float2(0.f, 0.f);
           if (t512 < K) s.cnt[t512] = 0;
           named_bar(3, EPI_THREADS);
           // ---- per-decoder row lists ----
@@ -394,15 +429,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
             int cand[2 * TC_MAX_M];
             int nc = 0;
             for (int m = 0; m < M; ++m) {
-              if (pt < nseg) cand[nc++] = s.sel[(m * 2 + 0) * WIN_PTS + pt];
-              if (pt >= 1) cand[nc++] = s.sel[(m * 2 + 1) * WIN_PTS + pt - 1];
+              if (pt < nseg) cand[nc++] = s.sel[(m * 2 + 0) * W + pt];
+              if (pt >= 1) cand[nc++] = s.sel[(m * 2 + 1) * W + pt - 1];
             }
             for (int i = 0; i < nc; ++i) {
               bool dup = false;
               for (int j = 0; j < i; ++j) dup |= (cand[j] == cand[i]);
               if (!dup) {
                 const int slot = atomicAdd(&s.cnt[cand[i]], 1);
-                s.rows[cand[i] * WIN_PTS + slot] = uint8_t(pt);
+                s.rows[cand[i] * W + slot] = uint16_t(pt);
               }
             }
           }
@@ -428,7 +463,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
             // tcgen05.ld/st are warp-collective (.sync.aligned): a warp takes part as soon as one of
             // its 32 rows is in use; unused lanes compute on point 0 and store nothing
             const bool wact = q0 + (warp & 3) * 32 < s.cnt[k];
-            const int pt = active ? s.rows[k * WIN_PTS + q0 + row] : 0;
+            const int pt = active ? s.rows[k * W + q0 + row] : 0;
             // small weights of decoder k were prefetched into swbuf[swsel]; prefetch the next item's
             cp_async_wait_all();
             named_bar(bar_id, GROUP_THREADS);
@@ -520,14 +555,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
               }
               for (int m = 0; m < (active ? M : 0); ++m) {
                 // role 0: this point is the left end of its segment; role 1: right end of the previous one
-                if (s.sel[(m * 2 + 0) * WIN_PTS + pt] == k) {
-                  float4* d = reinterpret_cast<float4*>(s.XD + (m * WIN_PTS + pt) * XD_STRIDE + xc0);
+                if (s.sel[(m * 2 + 0) * W + pt] == k) {
+                  float4* d = reinterpret_cast<float4*>(X1 + (m * W + pt) * XD_STRIDE + xc0);
 #pragma unroll
                   for (int q = 0; q < 8; ++q)
                     if (q < nq) d[q] = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
                 }
-                if (pt >= 1 && s.sel[(m * 2 + 1) * WIN_PTS + pt - 1] == k) {
-                  float4* d = reinterpret_cast<float4*>(X2 + (m * WIN_PTS + pt - 1) * XD_STRIDE + xc0);
+                if (pt >= 1 && s.sel[(m * 2 + 1) * W + pt - 1] == k) {
+                  float4* d = reinterpret_cast<float4*>(X2 + (m * W + pt - 1) * XD_STRIDE + xc0);
 #pragma unroll
                   for (int q = 0; q < 8; ++q)
                     if (q < nq) d[q] = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
@@ -540,10 +575,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
           // ======================= x2 - x1 and the energy =======================
           {
             float e = 0.f, l = 0.f;
-            for (int idx = t512; idx < M * WIN_PTS; idx += EPI_THREADS) {
-              const int r = idx & (WIN_PTS - 1);
+            for (int idx = t512; idx < M * W; idx += EPI_THREADS) {
+              const int r = idx % W;
               if (r < nseg) {
-                float4* d0 = reinterpret_cast<float4*>(s.XD + idx * XD_STRIDE);
+                float4* d0 = reinterpret_cast<float4*>(X1 + idx * XD_STRIDE);
                 const float4* d1 = reinterpret_cast<const float4*>(X2 + idx * XD_STRIDE);
                 float q = 0.f;
 #pragma unroll
@@ -559,7 +594,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
             }
             e = warp_sum(e);
             l = warp_sum(l);
-            if (lane == 0) { s.red[160 + ew] = e; s.red[176 + ew] = l; }
+            if (lane == 0) { s.red[320 + ew] = e; s.red[336 + ew] = l; }
           }
           if (GRAD) named_bar(3, EPI_THREADS);  // the differences are read by other threads below
 
@@ -569,7 +604,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
               const int k = ctl->item[it] & 0xFF, q0 = (ctl->item[it] >> 8) * 128;
               const bool active = q0 + row < s.cnt[k];
               const bool wact = q0 + (warp & 3) * 32 < s.cnt[k];
-              const int pt = active ? s.rows[k * WIN_PTS + q0 + row] : 0;
+              const int pt = active ? s.rows[k * W + q0 + row] : 0;
               cp_async_wait_all();
               named_bar(bar_id, GROUP_THREADS);
               const float* sw = swbuf + swsel * 576;
@@ -590,8 +625,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
 #pragma unroll
                 for (int j = 0; j < 32; ++j) g[j] = 0.f;
                 for (int m = 0; m < (active ? M : 0); ++m) {
-                  if (pt >= 1 && s.sel[(m * 2 + 1) * WIN_PTS + pt - 1] == k) {
-                    const float4* d = reinterpret_cast<const float4*>(s.XD + (m * WIN_PTS + pt - 1) * XD_STRIDE + xc0);
+                  if (pt >= 1 && s.sel[(m * 2 + 1) * W + pt - 1] == k) {
+                    const float4* d = reinterpret_cast<const float4*>(X1 + (m * W + pt - 1) * XD_STRIDE + xc0);
 #pragma unroll
                     for (int q = 0; q < 8; ++q)
                       if (q < nq) {
@@ -599,8 +634,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                         g[4 * q] += v.x; g[4 * q + 1] += v.y; g[4 * q + 2] += v.z; g[4 * q + 3] += v.w;
                       }
                   }
-                  if (s.sel[(m * 2 + 0) * WIN_PTS + pt] == k) {
-                    const float4* d = reinterpret_cast<const float4*>(s.XD + (m * WIN_PTS + pt) * XD_STRIDE + xc0);
+                  if (s.sel[(m * 2 + 0) * W + pt] == k) {
+                    const float4* d = reinterpret_cast<const float4*>(X1 + (m * W + pt) * XD_STRIDE + xc0);
 #pragma unroll
                     for (int q = 0; q < 8; ++q)
                       if (q < nq) {
@@ -659,7 +694,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                 // a point occurs at most once per item and the items of a chain run in order:
                 // plain read-modify-write, deterministic
                 if (active) {
-                  float2* dzp = &s.dzs[(chain_id * 2 + half) * WIN_PTS + pt];
+                  float2* dzp = &s.dzs[(chain_id * 2 + half) * W + pt];
                   float2 acc = *dzp;
                   acc.x += ax.x + ax.y;
                   acc.y += ay.x + ay.y;
@@ -670,12 +705,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
           }
           named_bar(3, EPI_THREADS);
           // ---- d(omega) += P^T dz over the points of the window, energy partials ----
-          if (GRAD && t512 < WIN_PTS) {
+          if (GRAD) {
+            // all 512 epilogue threads, one point each (W <= 512); threads beyond the window add zeros
             const int pt = t512;
             float P[MAX_KB];
-            design_row(p.t[min(seg0 + pt, T - 1)], n_poly, Kb, s.basis, P);
-            const float2 d0 = s.dzs[pt], d1 = s.dzs[WIN_PTS + pt], d2 = s.dzs[2 * WIN_PTS + pt], d3 = s.dzs[3 * WIN_PTS + pt];
-            const float dx = (d0.x + d1.x) + (d2.x + d3.x), dy = (d0.y + d1.y) + (d2.y + d3.y);
+            float dx = 0.f, dy = 0.f;
+            if (pt < W) {
+              design_row(p.t[min(seg0 + pt, T - 1)], n_poly, Kb, s.basis, P);
+              const float2 d0 = s.dzs[pt], d1 = s.dzs[W + pt], d2 = s.dzs[2 * W + pt], d3 = s.dzs[3 * W + pt];
+              dx = (d0.x + d1.x) + (d2.x + d3.x);
+              dy = (d0.y + d1.y) + (d2.y + d3.y);
+            } else {
+#pragma unroll
+              for (int k = 0; k < MAX_KB; ++k) P[k] = 0.f;
+            }
 #pragma unroll
             for (int k = 0; k < MAX_KB; ++k)
               if (k < Kb) {
@@ -685,14 +728,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
           }
           if (t512 == 0) {
             float ee = 0.f, ll = 0.f;
-            for (int w = 0; w < 16; ++w) { ee += s.red[160 + w]; ll += s.red[176 + w]; }
+            for (int w = 0; w < 16; ++w) { ee += s.red[320 + w]; ll += s.red[336 + w]; }
             e_tot += ee;
             l_tot += ll;
           }
           named_bar(3, EPI_THREADS);
           if (GRAD && t512 < 2 * Kb) {
             float g = 0.f;
-            for (int w = 0; w < 8; ++w) g += s.red[w * 20 + t512];
+            for (int w = 0; w < 16; ++w) g += s.red[w * 20 + t512];
             s.gacc[t512] += g;
           }
         }  // windows
@@ -728,9 +771,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
         p.omega[size_t(n) * 2 * Kb + t512] = s.om[t512];
         p.adam_m[size_t(n) * 2 * Kb + t512] = s.om[2 * MAX_KB + t512];
         p.adam_v[size_t(n) * 2 * Kb + t512] = s.om[4 * MAX_KB + t512];
+        __threadfence();
       }
       named_bar(3, EPI_THREADS);
-    }  // curves
+      if (t512 == 0) {
+        const unsigned int v = unsigned(chunk) + 1u;
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&queue[64 + n]), "r"(v) : "memory");
+      }
+    }  // work units
+    // tell the control warps that there is no more work
+    if (t512 == 0) {
+      s.ctl[wcount & 1].nitems = -1;
+      __threadfence_block();
+      mbar_arrive(win_ready);
+    }
     cp_async_wait_all();
 #ifdef VLG_TC_STATS
     if (tg == 0 && blockIdx.x < 1024) g_tc_stats[blockIdx.x * 8 + 4 + chain_id * 2] = w_acc;
@@ -754,9 +808,43 @@ static int tc_grid(int N) {
   return N < sms ? N : sms;
 }
 
-// per CTA: layer-2 ReLU mask bits [K+8 items][128 rows][4 words] + right-end outputs x2 [M][256][52] fp32
-size_t tc_workspace_bytes(int N, int, int K, int M) {
-  return size_t(tc_grid(N)) * (size_t(K + 8) * 2048 + size_t(M) * WIN_PTS * XD_STRIDE * 4);
+// Window length: as few 128-row items per curve as possible.  A decoder is drawn by a point with
+// probability p = 1 - (1 - 1/K)^(2M); its row count n in a window of W points is ~Binomial(W, p) and it
+// costs ceil(n/128) items.  Evaluate the expected item count for every admissible number of windows.
+static int tc_window_points(int T, int K, int M) {
+  const double p = 1.0 - pow(1.0 - 1.0 / K, 2.0 * M);
+  const int segs = T - 1;
+  if (const char* env = getenv("VLG_TC_WINDOW")) {  // tuning override: number of windows per curve
+    const int nwin = atoi(env);
+    if (nwin >= 1) {
+      const int w = (segs + nwin - 1) / nwin + 1;
+      if (w >= 2 && w <= TC_MAX_W && tc_stages(w, K, M) >= 2) return w;
+    }
+  }
+  int best_w = 0;
+  double best = 1e300;
+  for (int nwin = 1; nwin <= segs; ++nwin) {
+    const int w = (segs + nwin - 1) / nwin + 1;  // points per window
+    if (w > TC_MAX_W) continue;
+    const int nst = tc_stages(w, K, M);
+    if (nst >= 2) {
+      const double mean = w * p, sd = sqrt(w * p * (1.0 - p)) + 1e-9;
+      double items = 0.0;
+      for (int q = 0; q * 128 < w; ++q) items += 0.5 * erfc((q * 128 + 0.5 - mean) / (sd * 1.4142135623730951));  // P(n > 128 q)
+      double cost = nwin * (K * items + 0.35);  // + per-window fixed cost in item units
+      if (nst == 2) cost *= 1.04;               // a two-stage weight ring cannot hold a whole GEMM's weights
+      if (cost < best) { best = cost; best_w = w; }
+    }
+    if (w <= 128) break;
+  }
+  return best_w;  // 0: does not fit
+}
+
+// per CTA: layer-2 ReLU mask bits [K+16 items][128 rows][4 words] + right-end outputs x2 [M][W][52] fp32
+size_t tc_workspace_bytes(int N, int T, int K, int M) {
+  if (M > TC_MAX_M || K > TC_MAX_K) return 0;
+  const int W = tc_window_points(T, K, M);
+  return tc_queue_words(N) * 4 + size_t(tc_grid(N)) * (size_t(K + 16) * 2048 + size_t(M) * W * XD_STRIDE * 4);
 }
 
 #ifdef VLG_TC_STATS
@@ -768,20 +856,26 @@ extern "C" int vlg_debug_tc_stats(long long* host_out, int n) {
 cudaError_t launch_tc(const StepParams& p, bool grad, cudaStream_t stream) {
   if (p.precision != 1) return cudaErrorNotSupported;  // 3xTF32 not built yet
   if (p.M > TC_MAX_M || p.K > TC_MAX_K) return cudaErrorNotSupported;
-  const int nst = tc_stages(p.M, p.K);
+  const int W = tc_window_points(p.T, p.K, p.M);
+  if (W < 2) return cudaErrorNotSupported;
+  const int nst = tc_stages(W, p.K, p.M);
   if (nst < 2) return cudaErrorNotSupported;
   if (p.workspace == nullptr || p.workspace_bytes < tc_workspace_bytes(p.N, p.T, p.K, p.M)) return cudaErrorInvalidValue;
-  const size_t smem = tc_smem_fixed_bytes(p.M, p.K) + size_t(2) * nst * STAGE_BYTES;
+  const size_t smem = tc_smem_fixed_bytes(W, p.K, p.M) + size_t(2) * nst * STAGE_BYTES;
   const int grid = tc_grid(p.N);
-  cudaError_t e;
+  StepParams q = p;
+  const int nchunks = q.steps < 4 ? q.steps : 4;          // chunks of a curve per launch
+  q.unit_steps = (q.steps + nchunks - 1) / nchunks;
+  cudaError_t e = cudaMemsetAsync(p.workspace, 0, tc_queue_words(p.N) * 4, stream);
+  if (e != cudaSuccess) return e;
   if (grad) {
     e = cudaFuncSetAttribute(tc_curve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
-    tc_curve_kernel<true><<<grid, TC_THREADS, smem, stream>>>(p, nst);
+    tc_curve_kernel<true><<<grid, TC_THREADS, smem, stream>>>(q, nst, W);
   } else {
     e = cudaFuncSetAttribute(tc_curve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
-    tc_curve_kernel<false><<<grid, TC_THREADS, smem, stream>>>(p, nst);
+    tc_curve_kernel<false><<<grid, TC_THREADS, smem, stream>>>(q, nst, W);
   }
   return cudaGetLastError();
 }
