@@ -24,3 +24,12 @@ for i, nm in enumerate(names):
     if nm != "-":
         print(f"{nm:22s} mean {st[:, i].mean():12.0f} cycles  ({100 * st[:, i].mean() / st[:, 3].mean():5.1f}% of mma total)")
 
+
+ph = (ctypes.c_longlong * (nc * 32))()
+lib.vlg_debug_tc_phase.argtypes = [ctypes.c_void_p, ctypes.c_int]
+assert lib.vlg_debug_tc_phase(ph, nc) == 0
+ph = np.array(ph).reshape(nc, 32).astype(np.float64).mean(0)
+names = {0: "everything else", 1: "energy: L2 loads", 2: "energy: diff + sums", 3: "loop exit", 4: "warp sums + smem"}
+tot = sum(ph)
+for i, nm in names.items():
+    print(f"phase {nm:34s} {ph[i]:10.0f} cycles  {100*ph[i]/tot:5.1f}%")

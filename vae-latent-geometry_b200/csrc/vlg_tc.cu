@@ -120,6 +120,21 @@ struct WinCtl {
   uint16_t item[MAX_ITEMS];  // decoder | pass << 8
 };
 
+// Wait for the chain's accumulator.  VLG_TC_WAIT_MODE 0: every lane polls the mbarrier; 1: lane 0
+// polls and the warp reconverges on __syncwarp (32x fewer mbarrier probes in the memory queue).
+#ifndef VLG_TC_WAIT_MODE
+#define VLG_TC_WAIT_MODE 0
+#endif
+__device__ __forceinline__ void acc_wait(uint64_t* bar, uint32_t parity, int lane) {
+#if VLG_TC_WAIT_MODE == 1
+  if (lane == 0) mbar_wait(bar, parity);
+  __syncwarp();
+#else
+  (void)lane;
+  mbar_wait(bar, parity);
+#endif
+}
+
 struct TcSmem {
   unsigned char* ring;  // [chain][stage] 16 KB
   float* XD;            // [m][W][52]: left-end outputs x1, then (after the energy pass) x2 - x1
@@ -260,7 +275,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
       uint32_t ph[2] = {0, 0}, ph_a[2] = {0, 0};
       long long w_full = 0, w_issue = 0;
       STAT_T0();
+#ifndef VLG_TC_IDLE_NS
+#define VLG_TC_IDLE_NS 0
+#endif
+      bool served = true;
       while (!(fin[0] && fin[1])) {
+        // back off when nothing was ready: a tight mbarrier.test_wait loop floods the SM's memory
+        // instruction queue and throttles the epilogue warps' loads (seen as lg/mio stalls in ncu)
+        if (!served && VLG_TC_IDLE_NS > 0) __nanosleep(VLG_TC_IDLE_NS);
+        served = false;
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           if (fin[c]) continue;
@@ -275,6 +298,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
             if (ops_left[c] == 0) continue;
           }
           if (!mbar_test(&a_ready[c], ph_a[c])) continue;
+          served = true;
           ph_a[c] ^= 1;
           tc_fence_after();
           // op order inside a window: F2 F3 per item, then B3 B2 per item
@@ -504,7 +528,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
             tc_fence_before();
             mbar_arrive(&a_ready[chain_id]);
             // layer 2 epilogue: D2 (Y) -> relu(+b2) -> A2 (Y, in place), mask bits
-            { STAT_T0(); mbar_wait(&acc_ready[chain_id], ph_acc); STAT_ADD(w_acc); }
+            { STAT_T0(); acc_wait(&acc_ready[chain_id], ph_acc, lane); STAT_ADD(w_acc); }
             ph_acc ^= 1;
             tc_fence_after();
             if (wact) {
@@ -538,7 +562,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
             tc_fence_before();
             mbar_arrive(&a_ready[chain_id]);
             // layer 3 epilogue: D3 (X[0:64]) + b3 -> the slots of this point that drew decoder k
-            { STAT_T0(); mbar_wait(&acc_ready[chain_id], ph_acc); STAT_ADD(w_acc); }
+            { STAT_T0(); acc_wait(&acc_ready[chain_id], ph_acc, lane); STAT_ADD(w_acc); }
             ph_acc ^= 1;
             tc_fence_after();
             if (wact) {
@@ -573,23 +597,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
           named_bar(3, EPI_THREADS);
 
           // ======================= x2 - x1 and the energy =======================
+          // 16 lanes per (m, segment) entry, one 16-byte piece each, so the L2 reads of x2 are
+          // coalesced 208-byte rows; six entries per lane are in flight before the first is used.
           {
             float e = 0.f, l = 0.f;
-            for (int idx = t512; idx < M * W; idx += EPI_THREADS) {
-              const int r = idx % W;
-              if (r < nseg) {
-                float4* d0 = reinterpret_cast<float4*>(X1 + idx * XD_STRIDE);
-                const float4* d1 = reinterpret_cast<const float4*>(X2 + idx * XD_STRIDE);
-                float q = 0.f;
+            const int sub = lane & 15;
+            constexpr int NV = XD_STRIDE / 4;   // 13 float4 per row
+            constexpr int UNR = 6;
+            const int nent = M * W;
+            for (int base = ew * 2 + (lane >> 4); base < nent; base += 32 * UNR) {
+              float4 v[UNR];
 #pragma unroll
-                for (int c = 0; c < XD_STRIDE / 4; ++c) {
-                  const float4 u = d0[c], v = d1[c];
-                  const float4 a = make_float4(v.x - u.x, v.y - u.y, v.z - u.z, v.w - u.w);
-                  d0[c] = a;
-                  q = fmaf(a.x, a.x, q); q = fmaf(a.y, a.y, q); q = fmaf(a.z, a.z, q); q = fmaf(a.w, a.w, q);
+              for (int j = 0; j < UNR; ++j) {
+                const int ent = base + 32 * j;
+                const bool ok = ent < nent && (ent % W) < nseg && sub < NV;
+                v[j] = ok ? __ldcg(reinterpret_cast<const float4*>(X2 + ent * XD_STRIDE) + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+#pragma unroll
+              for (int j = 0; j < UNR; ++j) {
+                const int ent = base + 32 * j;
+                const bool ok = ent < nent && (ent % W) < nseg && sub < NV;
+                float q = 0.f;
+                if (ok) {
+                  float4* d0 = reinterpret_cast<float4*>(X1 + ent * XD_STRIDE) + sub;
+                  const float4 u = *d0;
+                  const float4 a = make_float4(v[j].x - u.x, v[j].y - u.y, v[j].z - u.z, v[j].w - u.w);
+                  *d0 = a;
+                  q = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(a.z, a.z, a.w * a.w)));
                 }
-                e += q;
-                l += sqrtf(q);
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+                if (sub == 0) { e += q; l += sqrtf(q); }
               }
             }
             e = warp_sum(e);
@@ -653,7 +691,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
               tc_fence_before();
               mbar_arrive(&a_ready[chain_id]);
               // dh2 = (G W3) * mask2 -> A4 (Y, in place)
-              { STAT_T0(); mbar_wait(&acc_ready[chain_id], ph_acc); STAT_ADD(w_acc); }
+              { STAT_T0(); acc_wait(&acc_ready[chain_id], ph_acc, lane); STAT_ADD(w_acc); }
               ph_acc ^= 1;
               tc_fence_after();
               if (wact) {
@@ -671,7 +709,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
               tc_fence_before();
               mbar_arrive(&a_ready[chain_id]);
               // dh1 = (dh2 W2) * mask1 (recomputed); dz[point] += dh1 W1 over this thread's 64 hidden units
-              { STAT_T0(); mbar_wait(&acc_ready[chain_id], ph_acc); STAT_ADD(w_acc); }
+              { STAT_T0(); acc_wait(&acc_ready[chain_id], ph_acc, lane); STAT_ADD(w_acc); }
               ph_acc ^= 1;
               tc_fence_after();
               if (wact) {
