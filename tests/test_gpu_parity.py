@@ -345,3 +345,35 @@ def test_tf32_is_deterministic_and_shard_independent(vlg):
     m = make_model(vlg, sub)
     e = vlg.optimize_splines(m, dec, t, 2, M=2, seed=5, curve_id0=42, precision="tf32")
     assert torch.equal(m.omega, outs[0][0][2:5]) and torch.equal(e, outs[0][1][2:5])
+
+
+def test_config5_shape_k64_npoly8_t256(vlg):
+    """BASELINE config 5 shapes at a size the oracle finishes instantly: 64-decoder ensemble with default
+    nn.Linear init, n_poly 8, T = 256 (the fp32 kernel keeps its ReLU masks in the workspace for K this
+    large; the tensor-core kernel runs one 256-point window per curve)."""
+    import torch.nn as nn
+    torch.manual_seed(0)
+    K, N, T, n_poly, M, S = 64, 20, 256, 8, 2, 2
+    nets = [nn.Sequential(nn.Linear(2, 128), nn.ReLU(), nn.Linear(128, 128), nn.ReLU(), nn.Linear(128, 50)) for _ in range(K)]
+    W = {}
+    for name, idx in (("1", 0), ("2", 2), ("3", 4)):
+        W["W" + name] = torch.stack([n_[idx].weight.detach() for n_ in nets]).numpy()
+        W["b" + name] = torch.stack([n_[idx].bias.detach() for n_ in nets]).numpy()
+    basis, _ = vlg.construct_nullspace_basis(n_poly)
+    g = dict(a=(torch.rand(N, 2) * 6 - 3).numpy(), b=(torch.rand(N, 2) * 6 - 3).numpy(),
+             omega_init=(0.1 * torch.randn(N, n_poly + 1, 2)).numpy(), basis=basis.numpy(), n_poly=n_poly, **W)
+    dec = make_decoders(vlg, g, K)
+    t = torch.linspace(0, 1, T, device="cuda")
+    seed, id0 = 99, 7
+    draws = np.stack([O.counter_draws(seed, np.arange(N) + id0, s_, T, M, K) for s_ in range(S)])
+    r = O.optimize_steps(g["a"].astype(np.float64), g["b"].astype(np.float64), g["omega_init"].astype(np.float64),
+                         g["basis"].astype(np.float64), Hh.tgrid(T, np.float64), n_poly, Hh.decoder_list(W, K, np.float64), draws, S)
+    out = {}
+    for prec in ("fp32", "tf32"):
+        model = make_model(vlg, g)
+        _, trace = vlg.optimize_splines(model, dec, t, S, M=M, seed=seed, curve_id0=id0, precision=prec, return_trace=True)
+        out[prec] = (trace.cpu().numpy(), model.omega.cpu().numpy())
+    assert np.abs(out["fp32"][0] / r["energy"] - 1).max() < 1e-5
+    assert np.abs(out["fp32"][1] - r["omega"]).max() < 5e-6
+    assert np.abs(np.sqrt(out["tf32"][0] / r["energy"]) - 1).max() < 5e-3   # random-init nets: smooth, small energies
+    assert np.abs(out["tf32"][1] - r["omega"]).max() < 0.25 * S * 1e-3 + 1e-6

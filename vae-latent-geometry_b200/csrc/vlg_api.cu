@@ -157,7 +157,7 @@ int vlg_pack_decoders(const float* W1, const float* b1, const float* W2, const f
 
 size_t vlg_workspace_bytes(int N, int T, int n_poly, int K_active, int M, int precision) {
   (void)n_poly;
-  if (precision == VLG_PRECISION_FP32) return 0;
+  if (precision == VLG_PRECISION_FP32) return vlg::simt_workspace_bytes(N, K_active, M);
   return vlg::tc_workspace_bytes(N, T, K_active, M);
 }
 

@@ -129,29 +129,40 @@ __device__ __forceinline__ Smem carve(unsigned char* base, int M, int K) {
   s.gacc = f; f += 2 * MAX_KB + 2;
   s.red = f; f += 8 * 20;
   s.sel = reinterpret_cast<uint8_t*>(f); f += MAX_M * 2 * 128 / 4;
-  s.mask2 = reinterpret_cast<uint8_t*>(f);
+  s.mask2 = reinterpret_cast<uint8_t*>(f);  // replaced by a workspace slice when K is too large for shared memory
   (void)K;
   return s;
 }
 
 }  // namespace
 
-size_t simt_smem_bytes(int M, int K) {
+static size_t simt_smem_base_bytes(int M) {
   size_t fl = 128 * 128 + 2 * BS_FLOATS + size_t(M) * 128 * DIFF_STRIDE + 576 + 256 + 256 + 128 + 64 +
               4 * MAX_NPOLY * MAX_KB + (3 * 2 * MAX_KB + 2) + (2 * MAX_KB + 2) + 8 * 20 + MAX_M * 2 * 128 / 4;
-  return fl * 4 + size_t(K) * 128 * 16;
+  return fl * 4;
+}
+static bool simt_masks_in_smem(int M, int K) { return simt_smem_base_bytes(M) + size_t(K) * 2048 <= 232448; }
+static int simt_grid(int N, int M, int K) {
+  if (simt_masks_in_smem(M, K)) return N;   // one CTA per curve, scheduled by the hardware
+  return N < 296 ? N : 296;                 // persistent CTAs, each with a mask slice in the workspace
+}
+size_t simt_smem_bytes(int M, int K) { return simt_smem_base_bytes(M) + (simt_masks_in_smem(M, K) ? size_t(K) * 2048 : 0); }
+// layer-2 ReLU mask bits [cta][K][128 rows][16 bytes] when they do not fit in shared memory
+size_t simt_workspace_bytes(int N, int K, int M) {
+  return simt_masks_in_smem(M, K) ? 0 : size_t(simt_grid(N, M, K)) * K * 2048;
 }
 
 template <bool GRAD>
 __global__ void __launch_bounds__(NTHREADS, 1) simt_curve_kernel(StepParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, lane = tid & 31, warp = tid >> 5;
-  const int n = blockIdx.x;
   const int M = p.M, K = p.K, T = p.T, n_poly = p.n_poly, Kb = p.Kb, X = p.X;
   Smem s = carve(smem_raw, M, K);
-
-  // ---- per-curve state -> shared ----
+  if (p.workspace != nullptr) s.mask2 = reinterpret_cast<uint8_t*>(p.workspace) + size_t(blockIdx.x) * K * 2048;
   for (int i = tid; i < 4 * n_poly * Kb; i += NTHREADS) s.basis[i] = p.basis[i];
+
+  for (int n = blockIdx.x; n < p.N; n += gridDim.x) {
+  // ---- per-curve state -> shared ----
   if (tid < 2 * Kb) {
     s.om[tid] = p.omega[size_t(n) * 2 * Kb + tid];
     if (GRAD) {
@@ -446,19 +457,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) simt_curve_kernel(StepParams p) {
     p.adam_m[size_t(n) * 2 * Kb + tid] = s.om[2 * MAX_KB + tid];
     p.adam_v[size_t(n) * 2 * Kb + tid] = s.om[4 * MAX_KB + tid];
   }
+  __syncthreads();
+  }  // curves of this CTA
 }
 
 cudaError_t launch_simt(const StepParams& p, bool grad, cudaStream_t stream) {
   const size_t smem = simt_smem_bytes(p.M, p.K);
+  const int grid = simt_grid(p.N, p.M, p.K);
+  StepParams q = p;
+  if (simt_masks_in_smem(p.M, p.K)) {
+    q.workspace = nullptr;
+  } else if (p.workspace == nullptr || p.workspace_bytes < simt_workspace_bytes(p.N, p.K, p.M)) {
+    return cudaErrorInvalidValue;
+  }
   cudaError_t e;
   if (grad) {
     e = cudaFuncSetAttribute(simt_curve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
-    simt_curve_kernel<true><<<p.N, NTHREADS, smem, stream>>>(p);
+    simt_curve_kernel<true><<<grid, NTHREADS, smem, stream>>>(q);
   } else {
     e = cudaFuncSetAttribute(simt_curve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
-    simt_curve_kernel<false><<<p.N, NTHREADS, smem, stream>>>(p);
+    simt_curve_kernel<false><<<grid, NTHREADS, smem, stream>>>(q);
   }
   return cudaGetLastError();
 }
