@@ -168,7 +168,7 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": rate, "unit": "spline-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * N_CURVES / rate,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(weights, args.gpus, "cpu"),
+        "config": dict(workload_config(weights, args.gpus, "gpu"), precision="fp32 (PyTorch CPU)"),
         "cpu_baseline": {"value": rate, "unit": "spline-steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": "spline-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

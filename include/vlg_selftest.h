@@ -20,6 +20,16 @@ extern "C" {
 int vlg_selftest_umma(const float* A, const float* Bimg, const float* Blo, float* D, int N, int K,
                       int b_mn_major, int split3, void* stream);
 
+/* Same with explicit descriptor strides (bytes; 0 = default) -- used to decode how the tensor core
+ * interprets a shared-memory matrix descriptor. */
+int vlg_selftest_umma_ex(const float* A, const float* Bimg, const float* Blo, float* D, int N, int K,
+                         int b_mn_major, int split3, int lbo, int sbo, int kstep, void* stream);
+
+/* Tensor-pipe rate probe: `iters` back-to-back kind::tf32 MMAs (M=128, K=8, A in TMEM) per CTA on `ctas`
+ * CTAs; out[cta] = clock64 cycles from first issue to mbarrier-observed completion.  mode bit0 adds
+ * concurrent TMEM ld/st traffic, bit1 concurrent shared-memory loads (interference study). */
+int vlg_selftest_mma_rate(int N, int iters, int lbo, int sbo, int ctas, int mode, long long* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

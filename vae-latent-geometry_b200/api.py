@@ -171,19 +171,14 @@ def compute_energy_mc(model: GeodesicSplineBatch, decoders: DecoderEnsemble, t_v
 def compute_energy(spline: GeodesicSplineBatch, decoder: DecoderEnsemble, t_vals: torch.Tensor,
                    precision: str = "fp32") -> torch.Tensor:
     """Deterministic single-decoder energy (src/single_decoder/optimize_energy_batched.py:51-57)."""
-    return compute_energy_mc(spline, decoder[:1], t_vals, M=1, draws=_zero_draws(spline, t_vals), precision=precision)
+    # one active decoder: every counter draw is 0, no draw tensor needed
+    return compute_energy_mc(spline, decoder[:1], t_vals, M=1, precision=precision)
 
 
 def compute_geodesic_lengths(spline: GeodesicSplineBatch, decoder: DecoderEnsemble, t_vals: torch.Tensor,
                              precision: str = "fp32") -> torch.Tensor:
     """Poly-line length in data space (src/single_decoder/optimize_energy_batched.py:42-49)."""
-    return compute_energy_mc(spline, decoder[:1], t_vals, M=1, draws=_zero_draws(spline, t_vals),
-                             precision=precision, return_length=True)[1]
-
-
-def _zero_draws(spline, t_vals):
-    return torch.zeros((1, 1, 2, t_vals.shape[0] - 1, spline.omega.shape[0]), dtype=torch.uint8,
-                       device=spline.omega.device)
+    return compute_energy_mc(spline, decoder[:1], t_vals, M=1, precision=precision, return_length=True)[1]
 
 
 def optimize_single_decoder(model: GeodesicSplineBatch, decoder: DecoderEnsemble, t_vals: torch.Tensor,
