@@ -25,11 +25,16 @@ for i, nm in enumerate(names):
         print(f"{nm:22s} mean {st[:, i].mean():12.0f} cycles  ({100 * st[:, i].mean() / st[:, 3].mean():5.1f}% of mma total)")
 
 
-ph = (ctypes.c_longlong * (nc * 32))()
+ph = (ctypes.c_longlong * (nc * 48))()
 lib.vlg_debug_tc_phase.argtypes = [ctypes.c_void_p, ctypes.c_int]
 assert lib.vlg_debug_tc_phase(ph, nc) == 0
-ph = np.array(ph).reshape(nc, 32).astype(np.float64).mean(0)
-names = {0: "everything else", 1: "energy: L2 loads", 2: "energy: diff + sums", 3: "loop exit", 4: "warp sums + smem"}
-tot = sum(ph)
-for i, nm in names.items():
-    print(f"phase {nm:34s} {ph[i]:10.0f} cycles  {100*ph[i]/tot:5.1f}%")
+ph = np.array(ph).reshape(nc, 2, 24).astype(np.float64).mean(0)
+names = ["window setup", "F: sw wait + layer 1 + st", "F: wait F2", "F: E-F2", "F: wait F3", "F: E-F3", "bar after forward",
+         "energy pass", "B: G build + st", "B: wait B3", "B: E-B3", "B: wait B2", "B: E-B2", "bar after backward",
+         "domega + reductions", "step prologue/Adam", "F: item setup", "F: cp wait + group bar", "B: item setup", "B: cp wait + group bar",
+         "B: zs/bits loads", "-", "-", "-"]
+for c in range(2):
+    tot = ph[c].sum()
+    print(f"chain {c}: total {tot:.0f} cycles")
+    for i, nm in enumerate(names):
+        print(f"   {nm:28s} {ph[c, i]:10.0f}  {100 * ph[c, i] / tot:5.1f}%")

@@ -44,11 +44,17 @@ namespace vlg {
 #ifdef VLG_TC_STATS
 // debug build only: per-CTA wait-cycle counters [cta][8]
 __device__ long long g_tc_stats[1024 * 8];
+__device__ long long g_tc_phase[1024 * 48];  // [cta][chain][24] cycles of epilogue thread 0 per phase
 #define STAT_T0() long long _t0 = clock64()
 #define STAT_ADD(var) var += clock64() - _t0
+#ifndef VLG_STAT_TG
+#define VLG_STAT_TG 0
+#endif
+#define PH(i) { const long long _now = clock64(); phc[i] += _now - tlast; tlast = _now; }
 #else
 #define STAT_T0()
 #define STAT_ADD(var)
+#define PH(i)
 #endif
 
 namespace {
@@ -122,6 +128,9 @@ struct WinCtl {
 
 // Wait for the chain's accumulator.  VLG_TC_WAIT_MODE 0: every lane polls the mbarrier; 1: lane 0
 // polls and the warp reconverges on __syncwarp (32x fewer mbarrier probes in the memory queue).
+#ifndef VLG_EXP
+#define VLG_EXP 0   // timing experiments only (results are wrong for values != 0)
+#endif
 #ifndef VLG_TC_WAIT_MODE
 #define VLG_TC_WAIT_MODE 0
 #endif
@@ -267,9 +276,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
     }
   } else if (warp == 2) {
     // ================= MMA issuer: serves whichever chain is ready =================
-    // The whole warp runs this loop convergently; one elected lane's tcgen05 instructions take effect.
-    {
-      const uint32_t leader = elect_one();
+    if (lane == 0) {
       int slot[2] = {0, 0}, opi[2] = {0, 0}, nitc[2] = {0, 0};
       int ops_left[2] = {0, 0};      // ops of the chain's current window still to issue
       long win[2] = {0, 0};          // next window whose item list the chain has to pick up
@@ -321,21 +328,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
               for (int ks = 0; ks < nk; ++ks) {
                 const uint64_t desc =
                     umma_smem_desc(sbase + uint32_t(ks) * 2u * uint32_t(oi.n) * 16u, uint32_t(oi.n) * 16u, 128u);
-                umma_tf32_ts_elect(chain + oi.d_col, chain + oi.a_col + uint32_t(st * oi.kper + ks * 8), desc, idesc,
-                                   (st | ks) ? 1u : 0u, leader);
+                umma_tf32_ts(chain + oi.d_col, chain + oi.a_col + uint32_t(st * oi.kper + ks * 8), desc, idesc,
+                             (st | ks) ? 1u : 0u);
               }
-              umma_commit_elect(&emptyc[slot[c]], leader);
+              umma_commit(&emptyc[slot[c]]);
               STAT_ADD(w_issue);
             }
             if (++slot[c] == nst) { slot[c] = 0; ph[c] ^= 1; }
           }
-          umma_commit_elect(&acc_ready[c], leader);
+          umma_commit(&acc_ready[c]);
           ++opi[c];
           --ops_left[c];
         }
       }
 #ifdef VLG_TC_STATS
-      if (lane == 0 && blockIdx.x < 1024) {
+      if (blockIdx.x < 1024) {
         g_tc_stats[blockIdx.x * 8 + 2] = w_full;
         g_tc_stats[blockIdx.x * 8 + 3] = clock64() - _t0;
         g_tc_stats[blockIdx.x * 8 + 5] = w_issue;
@@ -363,6 +370,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
     uint32_t ph_acc = 0;
     const float coefm = 2.0f / float(M);
     long long w_acc = 0;
+#ifdef VLG_TC_STATS
+    long long phc[24];
+    for (int i = 0; i < 24; ++i) phc[i] = 0;
+    long long tlast = clock64();
+#endif
     long wcount = 0;                            // windows processed by this CTA so far
     // this CTA's slice of the L2-resident workspace: layer-2 ReLU masks [item][row][4 words], then the
     // right-end decoder outputs x2 [m][W][52].  (The left-end outputs x1 / the differences stay in shared
@@ -418,6 +430,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
         float e_tot = 0.f, l_tot = 0.f;  // meaningful in t512 == 0
         named_bar(3, EPI_THREADS);
 
+        PH(15);
         for (int win = 0; win < nwin; ++win, ++wcount) {
           const int seg0 = win * WSEG;
           const int nseg = min(WSEG, T - 1 - seg0);
@@ -482,6 +495,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
           if (chain_id < nitems && tg < 144)
             cp_async16(swbuf + swsel * 576 + tg * 4, dec_ptr(p.packed, ctl->item[chain_id] & 0xFF) + tg * 4);
 
+          PH(0);
           // =============================== forward ===============================
           for (int it = chain_id; it < nitems; it += 2) {
             const int k = ctl->item[it] & 0xFF, q0 = (ctl->item[it] >> 8) * 128;
@@ -491,8 +505,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
             const bool wact = q0 + (warp & 3) * 32 < s.cnt[k];
             const int pt = active ? s.rows[k * W + q0 + row] : 0;
             // small weights of decoder k were prefetched into swbuf[swsel]; prefetch the next item's
+            PH(16);
             cp_async_wait_all();
             named_bar(bar_id, GROUP_THREADS);
+            PH(17);
             const float* sw = swbuf + swsel * 576;
             {
               int nx = it + 2;
@@ -529,10 +545,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
             tmem_wait_st();
             tc_fence_before();
             mbar_arrive(&a_ready[chain_id]);
+            PH(1);
             // layer 2 epilogue: D2 (Y) -> relu(+b2) -> A2 (Y, in place), mask bits
             { STAT_T0(); acc_wait(&acc_ready[chain_id], ph_acc, lane); STAT_ADD(w_acc); }
             ph_acc ^= 1;
             tc_fence_after();
+            PH(2);
             if (wact) {
               uint32_t v0[32], v1[32];
               tmem_ld32x2_sync(colY + col0, colY + col0 + 32, v0, v1);
@@ -563,10 +581,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
             tmem_wait_st();
             tc_fence_before();
             mbar_arrive(&a_ready[chain_id]);
+            PH(3);
             // layer 3 epilogue: D3 (X[0:64]) + b3 -> the slots of this point that drew decoder k
             { STAT_T0(); acc_wait(&acc_ready[chain_id], ph_acc, lane); STAT_ADD(w_acc); }
             ph_acc ^= 1;
             tc_fence_after();
+            PH(4);
             if (wact) {
               uint32_t xv[32];
               tmem_ld32_sync(colX + xc0, xv);
@@ -587,7 +607,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                   for (int q = 0; q < 8; ++q)
                     if (q < nq) d[q] = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
                 }
-                if (pt >= 1 && s.sel[(m * 2 + 1) * W + pt - 1] == k) {
+                if (VLG_EXP != 2 && pt >= 1 && s.sel[(m * 2 + 1) * W + pt - 1] == k) {
                   float4* d = reinterpret_cast<float4*>(X2 + (m * W + pt - 1) * XD_STRIDE + xc0);
 #pragma unroll
                   for (int q = 0; q < 8; ++q)
@@ -595,8 +615,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                 }
               }
             }
+            PH(5);
           }
           named_bar(3, EPI_THREADS);
+          PH(6);
 
           // ======================= x2 - x1 and the energy =======================
           // 16 lanes per (m, segment) entry, one 16-byte piece each, so the L2 reads of x2 are
@@ -613,7 +635,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
               for (int j = 0; j < UNR; ++j) {
                 const int ent = base + 32 * j;
                 const bool ok = ent < nent && (ent % W) < nseg && sub < NV;
+#if VLG_EXP == 1
+                v[j] = ok ? *(reinterpret_cast<const float4*>(X1 + ent * XD_STRIDE) + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+#else
                 v[j] = ok ? __ldcg(reinterpret_cast<const float4*>(X2 + ent * XD_STRIDE) + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+#endif
               }
 #pragma unroll
               for (int j = 0; j < UNR; ++j) {
@@ -637,16 +663,56 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
             if (lane == 0) { s.red[320 + ew] = e; s.red[336 + ew] = l; }
           }
           if (GRAD) named_bar(3, EPI_THREADS);  // the differences are read by other threads below
+          PH(7);
 
           if (GRAD) {
             // =============================== backward ===============================
+            // G = dE/dx_k of one item row (this thread's output columns) from the difference rows, as TF32
+            // bit patterns.  Built for item i+1 while B2 of item i is on the tensor core and held in
+            // registers until item i's last accumulator has been read.
+            auto build_g = [&](int it, uint32_t (&gv)[32]) {
+              const int k = ctl->item[it] & 0xFF, q0 = (ctl->item[it] >> 8) * 128;
+              const bool active = q0 + row < s.cnt[k];
+              const int pt = active ? s.rows[k * W + q0 + row] : 0;
+              float g[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) g[j] = 0.f;
+              for (int m = 0; m < (active ? M : 0); ++m) {
+                // right end of segment pt-1: +diff; left end of segment pt: -diff
+                if (pt >= 1 && s.sel[(m * 2 + 1) * W + pt - 1] == k) {
+                  const float4* d = reinterpret_cast<const float4*>(X1 + (m * W + pt - 1) * XD_STRIDE + xc0);
+#pragma unroll
+                  for (int q = 0; q < 8; ++q)
+                    if (q < nq) {
+                      const float4 v = d[q];
+                      g[4 * q] += v.x; g[4 * q + 1] += v.y; g[4 * q + 2] += v.z; g[4 * q + 3] += v.w;
+                    }
+                }
+                if (s.sel[(m * 2 + 0) * W + pt] == k) {
+                  const float4* d = reinterpret_cast<const float4*>(X1 + (m * W + pt) * XD_STRIDE + xc0);
+#pragma unroll
+                  for (int q = 0; q < 8; ++q)
+                    if (q < nq) {
+                      const float4 v = d[q];
+                      g[4 * q] -= v.x; g[4 * q + 1] -= v.y; g[4 * q + 2] -= v.z; g[4 * q + 3] -= v.w;
+                    }
+                }
+              }
+#pragma unroll
+              for (int j = 0; j < 32; ++j) gv[j] = tf32_round_bits(__float_as_uint(coefm * g[j]));
+            };
+            uint32_t gq[32];
+            if (chain_id < nitems) build_g(chain_id, gq);
             for (int it = chain_id; it < nitems; it += 2) {
               const int k = ctl->item[it] & 0xFF, q0 = (ctl->item[it] >> 8) * 128;
               const bool active = q0 + row < s.cnt[k];
               const bool wact = q0 + (warp & 3) * 32 < s.cnt[k];
               const int pt = active ? s.rows[k * W + q0 + row] : 0;
+              // all threads of the group are done with the previous item's accumulator (X) and small weights
+              PH(18);
               cp_async_wait_all();
               named_bar(bar_id, GROUP_THREADS);
+              PH(19);
               const float* sw = swbuf + swsel * 576;
               {
                 const int nx = it + 2;
@@ -656,46 +722,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
               swsel ^= 1;
               const float2 z = s.zs[pt];
               const float2 zx2 = make_float2(z.x, z.x), zy2 = make_float2(z.y, z.y);
-              // mask words for E-B3 (L2 round trip overlaps the G build and the first MMA)
+              // mask words for E-B3 (L2 round trip overlaps the first MMA)
               uint2 bits = make_uint2(0u, 0u);
               if (active) bits = *reinterpret_cast<const uint2*>(maskws + (it * 128 + row) * 4 + half * 2);
-              // G = dE/dx_k (this point), columns xc0 .. xc0+31 -> X[xc0 : xc0+32]
-              if (wact) {
-                float g[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) g[j] = 0.f;
-                for (int m = 0; m < (active ? M : 0); ++m) {
-                  if (pt >= 1 && s.sel[(m * 2 + 1) * W + pt - 1] == k) {
-                    const float4* d = reinterpret_cast<const float4*>(X1 + (m * W + pt - 1) * XD_STRIDE + xc0);
-#pragma unroll
-                    for (int q = 0; q < 8; ++q)
-                      if (q < nq) {
-                        const float4 v = d[q];
-                        g[4 * q] += v.x; g[4 * q + 1] += v.y; g[4 * q + 2] += v.z; g[4 * q + 3] += v.w;
-                      }
-                  }
-                  if (s.sel[(m * 2 + 0) * W + pt] == k) {
-                    const float4* d = reinterpret_cast<const float4*>(X1 + (m * W + pt) * XD_STRIDE + xc0);
-#pragma unroll
-                    for (int q = 0; q < 8; ++q)
-                      if (q < nq) {
-                        const float4 v = d[q];
-                        g[4 * q] -= v.x; g[4 * q + 1] -= v.y; g[4 * q + 2] -= v.z; g[4 * q + 3] -= v.w;
-                      }
-                  }
-                }
-                uint32_t v[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = tf32_round_bits(__float_as_uint(coefm * g[j]));
-                tmem_st32(colX + xc0, v);
-              }
+              PH(20);
+              if (wact) tmem_st32(colX + xc0, gq);
               tmem_wait_st();
               tc_fence_before();
               mbar_arrive(&a_ready[chain_id]);
+              PH(8);
               // dh2 = (G W3) * mask2 -> A4 (Y, in place)
               { STAT_T0(); acc_wait(&acc_ready[chain_id], ph_acc, lane); STAT_ADD(w_acc); }
               ph_acc ^= 1;
               tc_fence_after();
+              PH(9);
               if (wact) {
                 uint32_t v0[32], v1[32];
                 tmem_ld32x2_sync(colY + col0, colY + col0 + 32, v0, v1);
@@ -710,26 +750,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
               tmem_wait_st();
               tc_fence_before();
               mbar_arrive(&a_ready[chain_id]);
+              PH(10);
+              // while B2 runs: the next item's G
+              if (it + 2 < nitems) build_g(it + 2, gq);
               // dh1 = (dh2 W2) * mask1 (recomputed); dz[point] += dh1 W1 over this thread's 64 hidden units
               { STAT_T0(); acc_wait(&acc_ready[chain_id], ph_acc, lane); STAT_ADD(w_acc); }
               ph_acc ^= 1;
               tc_fence_after();
+              PH(11);
               if (wact) {
-                uint32_t v0[32], v1[32];
-                tmem_ld32x2_sync(colX + col0, colX + col0 + 32, v0, v1);
                 float2 ax = make_float2(0.f, 0.f), ay = make_float2(0.f, 0.f);
 #pragma unroll
-                for (int j = 0; j < 64; j += 2) {
-                  const int c = col0 + j;
-                  const float2 wx = *reinterpret_cast<const float2*>(sw + OFF_W1X + c);
-                  const float2 wy = *reinterpret_cast<const float2*>(sw + OFF_W1Y + c);
-                  const float2 bb = *reinterpret_cast<const float2*>(sw + OFF_B1 + c);
-                  const float2 h = __ffma2_rn(wy, zy2, __ffma2_rn(wx, zx2, bb));
-                  const uint32_t r0 = j < 32 ? v0[j] : v1[j - 32];
-                  const uint32_t r1 = j < 32 ? v0[j + 1] : v1[j - 31];
-                  const float2 dh = make_float2(h.x > 0.f ? __uint_as_float(r0) : 0.f, h.y > 0.f ? __uint_as_float(r1) : 0.f);
-                  ax = __ffma2_rn(dh, wx, ax);
-                  ay = __ffma2_rn(dh, wy, ay);
+                for (int c0 = 0; c0 < 64; c0 += 32) {
+                  uint32_t v[32];
+                  tmem_ld32_sync(colX + col0 + c0, v);
+#pragma unroll
+                  for (int j = 0; j < 32; j += 2) {
+                    const int c = col0 + c0 + j;
+                    const float2 wx = *reinterpret_cast<const float2*>(sw + OFF_W1X + c);
+                    const float2 wy = *reinterpret_cast<const float2*>(sw + OFF_W1Y + c);
+                    const float2 bb = *reinterpret_cast<const float2*>(sw + OFF_B1 + c);
+                    const float2 h = __ffma2_rn(wy, zy2, __ffma2_rn(wx, zx2, bb));
+                    const float2 dh = make_float2(h.x > 0.f ? __uint_as_float(v[j]) : 0.f, h.y > 0.f ? __uint_as_float(v[j + 1]) : 0.f);
+                    ax = __ffma2_rn(dh, wx, ax);
+                    ay = __ffma2_rn(dh, wy, ay);
+                  }
                 }
                 // a point occurs at most once per item and the items of a chain run in order:
                 // plain read-modify-write, deterministic
@@ -741,9 +786,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                   *dzp = acc;
                 }
               }
+              PH(12);
             }
           }
           named_bar(3, EPI_THREADS);
+          PH(13);
           // ---- d(omega) += P^T dz over the points of the window, energy partials ----
           if (GRAD) {
             // all 512 epilogue threads, one point each (W <= 512); threads beyond the window add zeros
@@ -778,6 +825,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
             for (int w = 0; w < 16; ++w) g += s.red[w * 20 + t512];
             s.gacc[t512] += g;
           }
+          PH(14);
         }  // windows
 
         named_bar(3, EPI_THREADS);
@@ -827,7 +875,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
     }
     cp_async_wait_all();
 #ifdef VLG_TC_STATS
-    if (tg == 0 && blockIdx.x < 1024) g_tc_stats[blockIdx.x * 8 + 4 + chain_id * 2] = w_acc;
+    if (tg == VLG_STAT_TG && blockIdx.x < 1024) {
+      g_tc_stats[blockIdx.x * 8 + 4 + chain_id * 2] = w_acc;
+      for (int i = 0; i < 24; ++i) g_tc_phase[(blockIdx.x * 2 + chain_id) * 24 + i] = phc[i];
+    }
 #endif
     (void)w_acc;
   }
@@ -890,6 +941,9 @@ size_t tc_workspace_bytes(int N, int T, int K, int M) {
 #ifdef VLG_TC_STATS
 extern "C" int vlg_debug_tc_stats(long long* host_out, int n) {
   return cudaMemcpyFromSymbol(host_out, g_tc_stats, size_t(n) * 8 * sizeof(long long)) == cudaSuccess ? 0 : -3;
+}
+extern "C" int vlg_debug_tc_phase(long long* host_out, int n) {
+  return cudaMemcpyFromSymbol(host_out, g_tc_phase, size_t(n) * 48 * sizeof(long long)) == cudaSuccess ? 0 : -3;
 }
 #endif
 

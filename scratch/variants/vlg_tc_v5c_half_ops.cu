@@ -44,11 +44,17 @@ namespace vlg {
 #ifdef VLG_TC_STATS
 // debug build only: per-CTA wait-cycle counters [cta][8]
 __device__ long long g_tc_stats[1024 * 8];
+__device__ long long g_tc_phase[1024 * 48];  // [cta][chain][24] cycles of one epilogue thread per phase
 #define STAT_T0() long long _t0 = clock64()
 #define STAT_ADD(var) var += clock64() - _t0
+#ifndef VLG_STAT_TG
+#define VLG_STAT_TG 0
+#endif
+#define PH(i) { const long long _now = clock64(); phc[i] += _now - tlast; tlast = _now; }
 #else
 #define STAT_T0()
 #define STAT_ADD(var)
+#define PH(i)
 #endif
 
 namespace {
@@ -82,6 +88,31 @@ __device__ __forceinline__ OpInfo op_info(int op) {
     case 1: return {OFF_W3_UMMA, 2, 64, 64, 128, 0};     // F3: D3(X[0:64]) = A2(Y) * W3^T
     case 2: return {OFF_W3T_UMMA, 2, 128, 32, 0, 128};   // B3: D4(Y) = G(X[0:64]) * W3
     default: return {OFF_W2T_UMMA, 4, 128, 32, 128, 0};  // B2: D5(X) = A4(Y) * W2
+  }
+}
+// K-CHUNK ORDER.  The epilogue threads write an A operand in two sub-passes (a thread owns 64 -- for G, 32 --
+// consecutive columns and stores their first half, then their second half), and the MMAs of the first
+// sub-pass's columns are issued while the second sub-pass is still being computed.  Ring stages are
+// therefore filled in the order the columns become ready: the first half of an op's stages holds the
+// contraction indices of sub-pass 0, the second half those of sub-pass 1.
+//   F2 / B2 (K = 128, thread columns 64h + 32j):   stage order K-blocks {0, 64 | 32, 96}, 32 wide
+//   F3      (K = 128, 64 per stage):               stage j = K {32j .. 32j+31} and {64+32j .. 64+32j+31}
+//   B3      (K = 64, thread columns 32h + 16j):    stage j = K {16j .. 16j+15} and {32+16j .. 32+16j+15}
+// A K-range [k0, k0+len) of a no-swizzle K-major image is the contiguous byte range k0*N*4 .. (k0+len)*N*4.
+__device__ __forceinline__ int op_pieces(int op) { return (op == 1 || op == 2) ? 2 : 1; }
+__device__ __forceinline__ int op_piece_k0(int op, int st, int piece) {
+  switch (op) {
+    case 1: return 64 * piece + 32 * st;
+    case 2: return 32 * piece + 16 * st;
+    default: return 32 * (((st & 1) << 1) | (st >> 1));  // 0, 64, 32, 96
+  }
+}
+// first contraction index of k-step ks (8 wide) of ring stage st
+__device__ __forceinline__ int op_kstep_k0(int op, int st, int ks) {
+  switch (op) {
+    case 1: return (ks < 4) ? 32 * st + 8 * ks : 64 + 32 * st + 8 * (ks - 4);
+    case 2: return (ks < 2) ? 16 * st + 8 * ks : 32 + 16 * st + 8 * (ks - 2);
+    default: return 32 * (((st & 1) << 1) | (st >> 1)) + 8 * ks;
   }
 }
 
@@ -150,12 +181,12 @@ struct TcSmem {
   float* om;            // 56
   float* gacc;          // 20
   float* red;           // 16*20 + 32
-  uint64_t* bars;       // full[2][MAX_STAGES], empty[2][MAX_STAGES], a_ready[2], acc_ready[2], win_ready
+  uint64_t* bars;       // full[2][MAX_STAGES], empty[2][MAX_STAGES], a_ready[2][2], acc_ready[2], win_ready
   uint32_t* tmem_base;  // [0] TMEM base address, [1] current work unit
 };
 
 constexpr int CTL_FLOATS = (2 * sizeof(WinCtl) + 3) / 4;
-constexpr int BAR_WORDS = 2 * (4 * MAX_STAGES + 5);
+constexpr int BAR_WORDS = 2 * (4 * MAX_STAGES + 7);
 
 __device__ __forceinline__ TcSmem tc_carve(unsigned char* base, int W, int K, int M, int nst) {
   TcSmem s;
@@ -203,9 +234,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
   const int WSEG = W - 1;  // segments per window
   uint64_t* full = s.bars;                       // [2][MAX_STAGES]
   uint64_t* empty = s.bars + 2 * MAX_STAGES;     // [2][MAX_STAGES]
-  uint64_t* a_ready = s.bars + 4 * MAX_STAGES;
-  uint64_t* acc_ready = s.bars + 4 * MAX_STAGES + 2;
-  uint64_t* win_ready = s.bars + 4 * MAX_STAGES + 4;
+  uint64_t* a_ready = s.bars + 4 * MAX_STAGES;          // [chain][sub-pass]
+  uint64_t* acc_ready = s.bars + 4 * MAX_STAGES + 4;
+  uint64_t* win_ready = s.bars + 4 * MAX_STAGES + 6;
   const int nwin = (T - 1 + WSEG - 1) / WSEG;
   // work queue (zeroed by the host before the launch): [0] next unit, [64 + n] chunks done of curve n
   unsigned int* queue = reinterpret_cast<unsigned int*>(p.workspace);
@@ -218,8 +249,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
     }
-    mbar_init(&a_ready[0], GROUP_THREADS);
-    mbar_init(&a_ready[1], GROUP_THREADS);
+    for (int i = 0; i < 4; ++i) mbar_init(&a_ready[i], GROUP_THREADS);
     mbar_init(&acc_ready[0], 1);
     mbar_init(&acc_ready[1], 1);
     mbar_init(win_ready, 1);
@@ -253,12 +283,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
           for (int i = c; i < nit; i += 2) {
             const int k = ctl->item[i] & 0xFF;
             for (int o = 0; o < 2; ++o) {
-              const OpInfo oi = op_info(phase * 2 + o);
+              const int op = phase * 2 + o;
+              const OpInfo oi = op_info(op);
               const char* src = reinterpret_cast<const char*>(dec_ptr(p.packed, k) + oi.img_off);
+              const int npc = op_pieces(op);
+              const uint32_t pc_bytes = STAGE_BYTES / npc;
               for (int st = 0; st < oi.nstages; ++st) {
                 mbar_wait(&emptyc[slot], ph ^ 1);
                 mbar_expect_tx(&fullc[slot], STAGE_BYTES);
-                bulk_g2s(ringc + slot * STAGE_BYTES, src + size_t(st) * STAGE_BYTES, STAGE_BYTES, &fullc[slot]);
+                for (int pc = 0; pc < npc; ++pc)
+                  bulk_g2s(ringc + slot * STAGE_BYTES + pc * pc_bytes, src + size_t(op_piece_k0(op, st, pc)) * oi.n * 4, pc_bytes,
+                           &fullc[slot]);
                 if (++slot == nst) { slot = 0; ph ^= 1; }
               }
             }
@@ -267,10 +302,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
     }
   } else if (warp == 2) {
     // ================= MMA issuer: serves whichever chain is ready =================
-    // The whole warp runs this loop convergently; one elected lane's tcgen05 instructions take effect.
-    {
-      const uint32_t leader = elect_one();
-      int slot[2] = {0, 0}, opi[2] = {0, 0}, nitc[2] = {0, 0};
+    if (lane == 0) {
+      int slot[2] = {0, 0}, opi[2] = {0, 0}, nitc[2] = {0, 0}, hop[2] = {0, 0};
       int ops_left[2] = {0, 0};      // ops of the chain's current window still to issue
       long win[2] = {0, 0};          // next window whose item list the chain has to pick up
       bool fin[2] = {false, false};
@@ -299,9 +332,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
             ++win[c];
             if (ops_left[c] == 0) continue;
           }
-          if (!mbar_test(&a_ready[c], ph_a[c])) continue;
+          // an op is issued in two halves: its first stages as soon as sub-pass 0 of the A operand is in TMEM
+          if (!mbar_test(&a_ready[c * 2 + hop[c]], ph_a[c])) continue;
           served = true;
-          ph_a[c] ^= 1;
           tc_fence_after();
           // op order inside a window: F2 F3 per item, then B3 B2 per item
           const int optype = (opi[c] < 2 * nitc[c]) ? (opi[c] & 1) : 2 + ((opi[c] - 2 * nitc[c]) & 1);
@@ -311,7 +344,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
           uint64_t* fullc = full + c * MAX_STAGES;
           uint64_t* emptyc = empty + c * MAX_STAGES;
           const unsigned char* ringc = s.ring + c * nst * STAGE_BYTES;
-          for (int st = 0; st < oi.nstages; ++st) {
+          const int st_lo = hop[c] * (oi.nstages / 2), st_hi = st_lo + oi.nstages / 2;
+          for (int st = st_lo; st < st_hi; ++st) {
             if (!mbar_test(&fullc[slot[c]], ph[c])) { STAT_T0(); mbar_wait(&fullc[slot[c]], ph[c]); STAT_ADD(w_full); }
             tc_fence_after();
             const uint32_t sbase = smem_u32(ringc + slot[c] * STAGE_BYTES);
@@ -321,21 +355,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
               for (int ks = 0; ks < nk; ++ks) {
                 const uint64_t desc =
                     umma_smem_desc(sbase + uint32_t(ks) * 2u * uint32_t(oi.n) * 16u, uint32_t(oi.n) * 16u, 128u);
-                umma_tf32_ts_elect(chain + oi.d_col, chain + oi.a_col + uint32_t(st * oi.kper + ks * 8), desc, idesc,
-                                   (st | ks) ? 1u : 0u, leader);
+                umma_tf32_ts(chain + oi.d_col, chain + oi.a_col + uint32_t(op_kstep_k0(optype, st, ks)), desc, idesc,
+                             (st | ks) ? 1u : 0u);
               }
-              umma_commit_elect(&emptyc[slot[c]], leader);
+              umma_commit(&emptyc[slot[c]]);
               STAT_ADD(w_issue);
             }
             if (++slot[c] == nst) { slot[c] = 0; ph[c] ^= 1; }
           }
-          umma_commit_elect(&acc_ready[c], leader);
-          ++opi[c];
-          --ops_left[c];
+          if (hop[c] == 0) {
+            hop[c] = 1;
+          } else {
+            umma_commit(&acc_ready[c]);
+            hop[c] = 0;
+            ph_a[c] ^= 1;
+            ++opi[c];
+            --ops_left[c];
+          }
         }
       }
 #ifdef VLG_TC_STATS
-      if (lane == 0 && blockIdx.x < 1024) {
+      if (blockIdx.x < 1024) {
         g_tc_stats[blockIdx.x * 8 + 2] = w_full;
         g_tc_stats[blockIdx.x * 8 + 3] = clock64() - _t0;
         g_tc_stats[blockIdx.x * 8 + 5] = w_issue;
@@ -363,6 +403,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
     uint32_t ph_acc = 0;
     const float coefm = 2.0f / float(M);
     long long w_acc = 0;
+#ifdef VLG_TC_STATS
+    long long phc[24];
+    for (int i = 0; i < 24; ++i) phc[i] = 0;
+    long long tlast = clock64();
+#endif
     long wcount = 0;                            // windows processed by this CTA so far
     // this CTA's slice of the L2-resident workspace: layer-2 ReLU masks [item][row][4 words], then the
     // right-end decoder outputs x2 [m][W][52].  (The left-end outputs x1 / the differences stay in shared
@@ -418,6 +463,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
         float e_tot = 0.f, l_tot = 0.f;  // meaningful in t512 == 0
         named_bar(3, EPI_THREADS);
 
+        PH(15);
         for (int win = 0; win < nwin; ++win, ++wcount) {
           const int seg0 = win * WSEG;
           const int nseg = min(WSEG, T - 1 - seg0);
@@ -482,6 +528,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
           if (chain_id < nitems && tg < 144)
             cp_async16(swbuf + swsel * 576 + tg * 4, dec_ptr(p.packed, ctl->item[chain_id] & 0xFF) + tg * 4);
 
+          PH(0);
           // =============================== forward ===============================
           for (int it = chain_id; it < nitems; it += 2) {
             const int k = ctl->item[it] & 0xFF, q0 = (ctl->item[it] >> 8) * 128;
@@ -524,15 +571,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                   v[j + 3] = relu_tf32(h1.y);
                 }
                 tmem_st32(colX + col0 + c0, v);
+                tmem_wait_st();
+                tc_fence_before();
+                mbar_arrive(&a_ready[chain_id * 2 + (c0 >> 5)]);
               }
+            } else {
+              mbar_arrive(&a_ready[chain_id * 2]);
+              mbar_arrive(&a_ready[chain_id * 2 + 1]);
             }
-            tmem_wait_st();
-            tc_fence_before();
-            mbar_arrive(&a_ready[chain_id]);
+            PH(1);
             // layer 2 epilogue: D2 (Y) -> relu(+b2) -> A2 (Y, in place), mask bits
             { STAT_T0(); acc_wait(&acc_ready[chain_id], ph_acc, lane); STAT_ADD(w_acc); }
             ph_acc ^= 1;
             tc_fence_after();
+            PH(2);
             if (wact) {
               uint32_t v0[32], v1[32];
               tmem_ld32x2_sync(colY + col0, colY + col0 + 32, v0, v1);
@@ -557,16 +609,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                 v1[j] = relu_tf32(q0f.x); v1[j + 1] = relu_tf32(q0f.y); v1[j + 2] = relu_tf32(q1f.x); v1[j + 3] = relu_tf32(q1f.y);
               }
               tmem_st32(colY + col0, v0);
+              tmem_wait_st();
+              tc_fence_before();
+              mbar_arrive(&a_ready[chain_id * 2]);
               tmem_st32(colY + col0 + 32, v1);
               if (GRAD && active) *reinterpret_cast<uint2*>(maskws + (it * 128 + row) * 4 + half * 2) = make_uint2(bits0, bits1);
+              tmem_wait_st();
+              tc_fence_before();
+              mbar_arrive(&a_ready[chain_id * 2 + 1]);
+            } else {
+              mbar_arrive(&a_ready[chain_id * 2]);
+              mbar_arrive(&a_ready[chain_id * 2 + 1]);
             }
-            tmem_wait_st();
-            tc_fence_before();
-            mbar_arrive(&a_ready[chain_id]);
+            PH(3);
             // layer 3 epilogue: D3 (X[0:64]) + b3 -> the slots of this point that drew decoder k
             { STAT_T0(); acc_wait(&acc_ready[chain_id], ph_acc, lane); STAT_ADD(w_acc); }
             ph_acc ^= 1;
             tc_fence_after();
+            PH(4);
             if (wact) {
               uint32_t xv[32];
               tmem_ld32_sync(colX + xc0, xv);
@@ -595,8 +655,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                 }
               }
             }
+            PH(5);
           }
           named_bar(3, EPI_THREADS);
+          PH(6);
 
           // ======================= x2 - x1 and the energy =======================
           // 16 lanes per (m, segment) entry, one 16-byte piece each, so the L2 reads of x2 are
@@ -637,6 +699,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
             if (lane == 0) { s.red[320 + ew] = e; s.red[336 + ew] = l; }
           }
           if (GRAD) named_bar(3, EPI_THREADS);  // the differences are read by other threads below
+          PH(7);
 
           if (GRAD) {
             // =============================== backward ===============================
@@ -684,18 +747,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                       }
                   }
                 }
-                uint32_t v[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = tf32_round_bits(__float_as_uint(coefm * g[j]));
-                tmem_st32(colX + xc0, v);
+                for (int h16 = 0; h16 < 2; ++h16) {
+                  uint32_t v[16];
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) v[j] = tf32_round_bits(__float_as_uint(coefm * g[16 * h16 + j]));
+                  tmem_st16(colX + xc0 + 16 * h16, v);
+                  tmem_wait_st();
+                  tc_fence_before();
+                  mbar_arrive(&a_ready[chain_id * 2 + h16]);
+                }
+              } else {
+                mbar_arrive(&a_ready[chain_id * 2]);
+                mbar_arrive(&a_ready[chain_id * 2 + 1]);
               }
-              tmem_wait_st();
-              tc_fence_before();
-              mbar_arrive(&a_ready[chain_id]);
+              PH(8);
               // dh2 = (G W3) * mask2 -> A4 (Y, in place)
               { STAT_T0(); acc_wait(&acc_ready[chain_id], ph_acc, lane); STAT_ADD(w_acc); }
               ph_acc ^= 1;
               tc_fence_after();
+              PH(9);
               if (wact) {
                 uint32_t v0[32], v1[32];
                 tmem_ld32x2_sync(colY + col0, colY + col0 + 32, v0, v1);
@@ -705,15 +776,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                   v1[j] = ((bits.y >> j) & 1u) ? tf32_round_bits(v1[j]) : 0u;
                 }
                 tmem_st32(colY + col0, v0);
+                tmem_wait_st();
+                tc_fence_before();
+                mbar_arrive(&a_ready[chain_id * 2]);
                 tmem_st32(colY + col0 + 32, v1);
+                tmem_wait_st();
+                tc_fence_before();
+                mbar_arrive(&a_ready[chain_id * 2 + 1]);
+              } else {
+                mbar_arrive(&a_ready[chain_id * 2]);
+                mbar_arrive(&a_ready[chain_id * 2 + 1]);
               }
-              tmem_wait_st();
-              tc_fence_before();
-              mbar_arrive(&a_ready[chain_id]);
+              PH(10);
               // dh1 = (dh2 W2) * mask1 (recomputed); dz[point] += dh1 W1 over this thread's 64 hidden units
               { STAT_T0(); acc_wait(&acc_ready[chain_id], ph_acc, lane); STAT_ADD(w_acc); }
               ph_acc ^= 1;
               tc_fence_after();
+              PH(11);
               if (wact) {
                 uint32_t v0[32], v1[32];
                 tmem_ld32x2_sync(colX + col0, colX + col0 + 32, v0, v1);
@@ -741,9 +820,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                   *dzp = acc;
                 }
               }
+              PH(12);
             }
           }
           named_bar(3, EPI_THREADS);
+          PH(13);
           // ---- d(omega) += P^T dz over the points of the window, energy partials ----
           if (GRAD) {
             // all 512 epilogue threads, one point each (W <= 512); threads beyond the window add zeros
@@ -778,6 +859,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
             for (int w = 0; w < 16; ++w) g += s.red[w * 20 + t512];
             s.gacc[t512] += g;
           }
+          PH(14);
         }  // windows
 
         named_bar(3, EPI_THREADS);
@@ -827,7 +909,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
     }
     cp_async_wait_all();
 #ifdef VLG_TC_STATS
-    if (tg == 0 && blockIdx.x < 1024) g_tc_stats[blockIdx.x * 8 + 4 + chain_id * 2] = w_acc;
+    if (tg == VLG_STAT_TG && blockIdx.x < 1024) {
+      g_tc_stats[blockIdx.x * 8 + 4 + chain_id * 2] = w_acc;
+      for (int i = 0; i < 24; ++i) g_tc_phase[(blockIdx.x * 2 + chain_id) * 24 + i] = phc[i];
+    }
 #endif
     (void)w_acc;
   }
@@ -890,6 +975,9 @@ size_t tc_workspace_bytes(int N, int T, int K, int M) {
 #ifdef VLG_TC_STATS
 extern "C" int vlg_debug_tc_stats(long long* host_out, int n) {
   return cudaMemcpyFromSymbol(host_out, g_tc_stats, size_t(n) * 8 * sizeof(long long)) == cudaSuccess ? 0 : -3;
+}
+extern "C" int vlg_debug_tc_phase(long long* host_out, int n) {
+  return cudaMemcpyFromSymbol(host_out, g_tc_phase, size_t(n) * 48 * sizeof(long long)) == cudaSuccess ? 0 : -3;
 }
 #endif
 

@@ -223,6 +223,9 @@ def test_errors_are_loud(vlg):
     t = torch.linspace(0, 1, 130, device="cuda")
     with pytest.raises(vlg.VlgError):
         vlg.optimize_splines(model, dec, t, 1, M=9, precision="fp32")        # M too large
+    with pytest.warns(UserWarning):                                          # M = 3: tf32 request served by the fp32 kernel
+        e3 = vlg.optimize_splines(make_model(vlg, g), dec, t, 1, M=3, seed=1, precision="tf32")
+    assert torch.equal(e3, vlg.optimize_splines(make_model(vlg, g), dec, t, 1, M=3, seed=1, precision="fp32"))
     with pytest.raises(vlg.VlgError):
         vlg.optimize_splines(model, dec, t.cpu(), 1, M=1, precision="fp32")  # CPU tensor
     with pytest.raises(vlg.VlgError):
@@ -377,3 +380,30 @@ def test_config5_shape_k64_npoly8_t256(vlg):
     assert np.abs(out["fp32"][1] - r["omega"]).max() < 5e-6
     assert np.abs(np.sqrt(out["tf32"][0] / r["energy"]) - 1).max() < 5e-3   # random-init nets: smooth, small energies
     assert np.abs(out["tf32"][1] - r["omega"]).max() < 0.25 * S * 1e-3 + 1e-6
+
+
+@pytest.mark.parametrize("prec,tol", [("fp32", 1e-3), ("tf32", 1e-3)])
+def test_full_config1_1000_steps_final_lengths(vlg, prec, tol):
+    """North-star statement: BASELINE config 1 at full length (45 curves, K=10, M=2, T=2000, 1000 Adam
+    steps) against the reference's own fp64 run with the same counter-based draws
+    (tests/golden/make_golden_full1000.py).  Free-running, so this bounds the accumulated drift of the
+    whole trajectory, not one step."""
+    path = Hh.GOLDEN / "ens_seed12_full1000.npz"
+    if not path.exists():
+        pytest.skip("golden not generated (tests/golden/make_golden_full1000.py, ~1 h of CPU)")
+    g = dict(np.load(path))
+    s = Hh.load("splines_seed12_euclidean_10")
+    inp = dict(a=s["a"], b=s["b"], omega_init=s["omega_init"], basis=s["basis"], n_poly=int(s["n_poly"]))
+    model = make_model(vlg, inp)
+    dec = make_decoders(vlg, Hh.load("evae_seed12_decoders"), 10)
+    t = torch.linspace(0, 1, 2000, device="cuda")
+    steps = int(g["steps"])
+    _, trace = vlg.optimize_splines(model, dec, t, steps, M=2, seed=int(g["seed"]), curve_id0=0, precision=prec,
+                                    return_trace=True)
+    trace = trace.cpu().numpy()
+    for i, st in enumerate(g["energy_steps"]):
+        rel = np.abs(np.sqrt(trace[int(st)] / g["energy_f64"][i]) - 1).max()
+        print(f"{prec}: step {int(st):4d} max rel length err vs reference fp64 = {rel:.2e}")
+    final = np.abs(np.sqrt(trace[-1]) / g["final_length_f64"] - 1).max()
+    assert final < tol, final
+    assert np.abs(model.omega.cpu().numpy() - g["omega_f64"]).max() < 5e-2

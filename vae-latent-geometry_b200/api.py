@@ -126,6 +126,21 @@ def _prep_draws(draws, N: int, steps: int, M: int, T: int, device) -> Optional[t
     return d.to(device=device, dtype=torch.uint8).permute(4, 0, 1, 2, 3).contiguous()
 
 
+TC_MAX_M, TC_MAX_K = 2, 64   # limits of the tensor-core kernel (csrc/vlg_tc.cu)
+
+
+def _resolve_precision(precision: str, decoders, M: int) -> int:
+    """'tf32' falls back to the fp32 CUDA-core kernel for shapes the tensor-core kernel is not built for
+    (M > 2 MC samples or more than 64 decoders) and for a single active decoder, where TF32 cannot
+    resolve the tiny adjacent-point differences (SURVEY hard part 1).  Still a GPU kernel -- there is no
+    CPU path."""
+    if precision == "tf32" and (M > TC_MAX_M or len(decoders) > TC_MAX_K):
+        import warnings
+        warnings.warn(f"tensor-core kernel supports M <= {TC_MAX_M}, K <= {TC_MAX_K}; using the fp32 kernel")
+        precision = "fp32"
+    return ops.PRECISIONS[precision]
+
+
 def _workspace(model, decoders, T, M, precision):
     n = ops.workspace_bytes(model.omega.shape[0], T, model.n_poly, len(decoders), M, precision)
     return torch.empty(n, dtype=torch.uint8, device=model.omega.device) if n else None
@@ -140,7 +155,7 @@ def optimize_splines(model: GeodesicSplineBatch, decoders: DecoderEnsemble, t_va
     last step [N] (src/optimize.py:168) and, optionally, the per-step energies [steps,N]."""
     N = model.omega.shape[0]
     T = t_vals.shape[0]
-    prec = ops.PRECISIONS[precision]
+    prec = _resolve_precision(precision, decoders, M)
     dev = model.omega.device
     energy = torch.empty(N, dtype=torch.float32, device=dev)
     trace = torch.empty((steps, N), dtype=torch.float32, device=dev) if return_trace else None
@@ -158,7 +173,7 @@ def compute_energy_mc(model: GeodesicSplineBatch, decoders: DecoderEnsemble, t_v
     """MC ensemble curve energy [N] (src/optimize.py:38-75), forward only."""
     N = model.omega.shape[0]
     T = t_vals.shape[0]
-    prec = ops.PRECISIONS[precision]
+    prec = _resolve_precision(precision, decoders, M)
     dev = model.omega.device
     energy = torch.empty(N, dtype=torch.float32, device=dev)
     length = torch.empty(N, dtype=torch.float32, device=dev) if return_length else None

@@ -128,13 +128,14 @@ namespace vlg {
 namespace {
 __global__ void __launch_bounds__(384) mma_rate_kernel(int N, int iters, int lbo, int sbo, int mode, long long* out) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ __align__(8) uint64_t bar_mma;
+  __shared__ __align__(8) uint64_t bar_mma, bar_scratch;
   __shared__ uint32_t tmem_base_s;
   __shared__ volatile int done;
   const int tid = threadIdx.x, warp = tid >> 5;
   for (int i = tid; i < 144 * 128; i += blockDim.x) reinterpret_cast<float*>(smem)[i] = 1.0f;
   if (tid == 0) {
     tc::mbar_init(&bar_mma, 1);
+    tc::mbar_init(&bar_scratch, 1);
     tc::fence_mbar_init();
     done = 0;
   }
@@ -148,19 +149,48 @@ __global__ void __launch_bounds__(384) mma_rate_kernel(int N, int iters, int lbo
     const uint32_t idesc = tc::umma_idesc_tf32(N, 0);
     const uint32_t sb = tc::smem_u32(smem);
     const long long t0 = clock64();
+    // mode bits 5..7: commit to a scratch mbarrier every 4 MMAs (32), switch the accumulator between two
+    // column ranges every 8 MMAs (64), start a fresh accumulation (accumulate = 0) every 16 MMAs (128)
     for (int i = 0; i < iters; ++i) {
       const int ks = i & 7;
       const uint64_t desc = tc::umma_smem_desc(sb + uint32_t(ks) * 2u * uint32_t(lbo), uint32_t(lbo), uint32_t(sbo));
-      tc::umma_tf32_ts(tmem + 128u, tmem + uint32_t(ks) * 8u, desc, idesc, 1u);
+      const uint32_t dcol = ((mode & 64) && ((i >> 3) & 1)) ? 256u : 128u;
+      tc::umma_tf32_ts(tmem + dcol, tmem + uint32_t(ks) * 8u, desc, idesc, ((mode & 128) && (i & 15) == 0) ? 0u : 1u);
+      if ((mode & 32) && (i & 3) == 3) tc::umma_commit(&bar_scratch);
     }
     tc::umma_commit(&bar_mma);
     tc::mbar_wait(&bar_mma, 0);
     out[blockIdx.x] = clock64() - t0;
+    if (iters > 0 && (mode & 16)) {
+      // completion latency of one MMA + commit issued into an idle pipe
+      const long long t1 = clock64();
+      tc::umma_tf32_ts(tmem + 128u, tmem, tc::umma_smem_desc(sb, uint32_t(lbo), uint32_t(sbo)), idesc, 1u);
+      tc::umma_commit(&bar_mma);
+      tc::mbar_wait(&bar_mma, 1);
+      out[2 * gridDim.x + blockIdx.x] = clock64() - t1;
+    }
     done = 1;
   } else if (warp >= 4) {
     // interference generators: mode bit0 = TMEM ld/st traffic (columns 384..447), bit1 = shared-memory loads
     const uint32_t lane_addr = uint32_t((warp & 3) * 32) << 16;
     float acc = 0.f;
+    if (mode & 4) {
+      // latency of a TMEM load+store round trip while the MMA stream runs (or not: iters = 0):
+      // 256 back-to-back {ld x32, wait, st x32, wait}; warps 4..7 only when bit3 is set
+      if (!(mode & 8) || warp < 8) {
+        const uint32_t col = tmem + lane_addr + 384u + uint32_t((warp >> 2) & 1) * 32u;
+        const long long t0 = clock64();
+        for (int it = 0; it < 256; ++it) {
+          uint32_t v[32];
+          tc::tmem_ld32_sync(col, v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += 1u;
+          tc::tmem_st32(col, v);
+          tc::tmem_wait_st();
+        }
+        if (tid == 128) out[gridDim.x + blockIdx.x] = clock64() - t0;
+      }
+    } else
     while (!done) {
       if (mode & 1) {
         uint32_t v[32];
