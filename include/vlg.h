@@ -46,7 +46,10 @@ enum {
 enum {
   VLG_PRECISION_FP32 = 0,   /* CUDA-core FFMA, fp32 accumulate: the <=1e-4/step variant     */
   VLG_PRECISION_TF32 = 1,   /* tcgen05.mma kind::tf32, fp32 accumulate in TMEM              */
-  VLG_PRECISION_TF32X3 = 2  /* 3xTF32 split (hi*hi + hi*lo + lo*hi): fp32-grade, tensor pipe */
+  VLG_PRECISION_TF32X3 = 2, /* 3xTF32 split (hi*hi + hi*lo + lo*hi): reserved, VLG_ERR_UNSUPPORTED */
+  VLG_PRECISION_F16 = 3     /* tcgen05.mma kind::f16: fp16 operands (11-bit significand, as TF32; backward
+                               quantities pre-scaled by 2^6), fp32 accumulate in TMEM: half the tensor-pipe
+                               time and weight traffic of TF32 for the same <=1e-3 length tolerance     */
 };
 
 const char* vlg_error_string(int code);

@@ -25,6 +25,10 @@ int vlg_selftest_umma(const float* A, const float* Bimg, const float* Blo, float
 int vlg_selftest_umma_ex(const float* A, const float* Bimg, const float* Blo, float* D, int N, int K,
                          int b_mn_major, int split3, int lbo, int sbo, int kstep, void* stream);
 
+/* D[128,N] = fp16(A[128,K]) * fp16(B)^T with tcgen05.mma kind::f16, fp32 accumulate.  A (fp32, device) is
+ * converted to fp16 pairs in TMEM (two k per 32-bit column); Bimg16 is the fp16 image img16[(k/8)*N + n][k%8]. */
+int vlg_selftest_umma_f16(const float* A, const void* Bimg16, float* D, int N, int K, void* stream);
+
 /* Tensor-pipe rate probe: `iters` back-to-back kind::tf32 MMAs (M=128, K=8, A in TMEM) per CTA on `ctas`
  * CTAs; out[cta] = clock64 cycles from first issue to mbarrier-observed completion.  mode bit0 adds
  * concurrent TMEM ld/st traffic, bit1 concurrent shared-memory loads (interference study). */

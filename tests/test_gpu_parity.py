@@ -233,15 +233,18 @@ def test_errors_are_loud(vlg):
 
 
 # ---------------------------------------------------------------------------------------------
-# tensor-core (tcgen05 kind::tf32) variant.  north_star tolerance: <= 1e-3 relative on geodesic
-# lengths (sqrt(E)), i.e. <= 2e-3 on energies.
+# tensor-core variants (tcgen05 kind::tf32, and kind::f16 with fp16 operands -- the same 11-bit
+# significand).  north_star tolerance: <= 1e-3 relative on geodesic lengths (sqrt(E)), i.e. <= 2e-3
+# on energies.
 # ---------------------------------------------------------------------------------------------
 TF32_LENGTH_TOL = 1e-3
+TC_PRECISIONS = ["tf32", "f16"]
 
 
 @pytest.mark.parametrize("tag", ["ens_seed12_euclid", "ens_seed12_entropy", "ens_seed12_cov_k3", "synth_np8_T256",
                                  "synth_np4_T130"])
-def test_tf32_steps_track_reference(vlg, tag):
+@pytest.mark.parametrize("tc", TC_PRECISIONS)
+def test_tf32_steps_track_reference(vlg, tag, tc):
     g = Hh.load(tag)
     K, T, M, S = int(g["K"]), int(g["T"]), int(g["M"]), int(g["steps"])
     if M > 2:
@@ -250,7 +253,7 @@ def test_tf32_steps_track_reference(vlg, tag):
     model = make_model(vlg, g)
     dec = make_decoders(vlg, g, K)
     t = torch.linspace(0, 1, T, device="cuda")
-    e_last, trace = vlg.optimize_splines(model, dec, t, S, M=M, draws=draws, precision="tf32", return_trace=True)
+    e_last, trace = vlg.optimize_splines(model, dec, t, S, M=M, draws=draws, precision=tc, return_trace=True)
     trace = trace.cpu().numpy()
     len_rel = np.abs(np.sqrt(trace / g["energy_f64"]) - 1).max()
     assert len_rel < TF32_LENGTH_TOL, len_rel
@@ -259,10 +262,11 @@ def test_tf32_steps_track_reference(vlg, tag):
     # Adam normalises the gradient, so near-zero gradient components turn tiny errors into
     # +-lr-sized steps: after S steps omega may differ by a fraction of S*lr = S*1e-3
     assert np.abs(model.omega.cpu().numpy() - g["omega_f64"]).max() < 0.25 * S * 1e-3
-    print(f"{tag}: tf32 max rel length err {len_rel:.2e}")
+    print(f"{tag}: {tc} max rel length err {len_rel:.2e}")
 
 
-def test_tf32_forward_energy_full_size(vlg):
+@pytest.mark.parametrize("tc", TC_PRECISIONS)
+def test_tf32_forward_energy_full_size(vlg, tc):
     s = Hh.load("splines_seed12_entropy_10")
     g = dict(a=s["a"], b=s["b"], omega_init=s["omega_init"], basis=s["basis"], n_poly=int(s["n_poly"]))
     N, T, K, M = 45, 2000, 10, 2
@@ -270,11 +274,11 @@ def test_tf32_forward_energy_full_size(vlg):
     dec = make_decoders(vlg, Hh.load("evae_seed12_decoders"), K)
     t = torch.linspace(0, 1, T, device="cuda")
     e32 = vlg.compute_energy_mc(model, dec, t, M=M, seed=3, step=7, precision="fp32").cpu().numpy()
-    etc = vlg.compute_energy_mc(model, dec, t, M=M, seed=3, step=7, precision="tf32").cpu().numpy()
+    etc = vlg.compute_energy_mc(model, dec, t, M=M, seed=3, step=7, precision=tc).cpu().numpy()
     assert np.abs(np.sqrt(etc / e32) - 1).max() < TF32_LENGTH_TOL
 
 
-@pytest.mark.parametrize("prec,tol", [("fp32", 2e-5), ("tf32", TF32_LENGTH_TOL)])
+@pytest.mark.parametrize("prec,tol", [("fp32", 2e-5), ("tf32", TF32_LENGTH_TOL), ("f16", TF32_LENGTH_TOL)])
 def test_final_length_after_150_steps(vlg, prec, tol):
     """Long horizon (free-running, not teacher-forced): final sqrt(E) against the reference's own
     fp64 run with the same recorded draws.  The reference's fp32-vs-fp64 gap is printed beside it."""
@@ -296,7 +300,8 @@ def test_final_length_after_150_steps(vlg, prec, tol):
 
 @pytest.mark.parametrize("T,N,K,M,n_poly", [(2, 1, 1, 1, 1), (3, 2, 2, 2, 2), (128, 3, 3, 2, 4), (255, 2, 5, 1, 8),
                                            (256, 1, 16, 2, 4), (257, 2, 4, 2, 4), (600, 3, 1, 1, 4), (513, 150, 7, 2, 4)])
-def test_tf32_edge_shapes_against_fp32_kernel(vlg, T, N, K, M, n_poly):
+@pytest.mark.parametrize("tc", TC_PRECISIONS)
+def test_tf32_edge_shapes_against_fp32_kernel(vlg, T, N, K, M, n_poly, tc):
     """Window boundaries (255/256/257 points), a decoder drawn by more than 128 points of a window
     (K=1: two 128-row items per window), a single segment, more curves than SMs (persistent CTAs
     walk several curves), K up to 16.  Compared against the fp32 kernel on identical draws."""
@@ -313,7 +318,7 @@ def test_tf32_edge_shapes_against_fp32_kernel(vlg, T, N, K, M, n_poly):
     dec = make_decoders(vlg, g, K)
     t = torch.linspace(0, 1, T, device="cuda")
     res = {}
-    for prec in ("fp32", "tf32"):
+    for prec in ("fp32", tc):
         model = make_model(vlg, g)
         _, trace = vlg.optimize_splines(model, dec, t, S, M=M, seed=11, curve_id0=5, precision=prec, return_trace=True)
         e, ln = vlg.compute_energy_mc(model, dec, t, M=M, seed=11, step=S, curve_id0=5, precision=prec,
@@ -326,27 +331,28 @@ def test_tf32_edge_shapes_against_fp32_kernel(vlg, T, N, K, M, n_poly):
     # inadequate there (SURVEY hard part 1: ~13 % mean error) -- that path is served by the fp32 kernel;
     # here it only has to be structurally right (same order of magnitude)
     tol = 0.5 if K == 1 else 2e-2
-    assert np.abs(res["tf32"][0] / res["fp32"][0] - 1).max() < tol
-    assert np.abs(res["tf32"][2] / res["fp32"][2] - 1).max() < tol
-    assert np.abs(res["tf32"][3] / res["fp32"][3] - 1).max() < tol
+    assert np.abs(res[tc][0] / res["fp32"][0] - 1).max() < tol
+    assert np.abs(res[tc][2] / res["fp32"][2] - 1).max() < tol
+    assert np.abs(res[tc][3] / res["fp32"][3] - 1).max() < tol
     # Adam's first steps move every coefficient by ~lr whatever the gradient size, so a sign flip of a
     # near-zero gradient component costs up to 2*lr per step; frequent for K = 1 (noisy TF32 gradient)
-    assert np.abs(res["tf32"][1] - res["fp32"][1]).max() < (2.0 if K == 1 else 0.25) * S * 1e-3 + 1e-6
+    assert np.abs(res[tc][1] - res["fp32"][1]).max() < (2.0 if K == 1 else 0.25) * S * 1e-3 + 1e-6
 
 
-def test_tf32_is_deterministic_and_shard_independent(vlg):
+@pytest.mark.parametrize("tc", TC_PRECISIONS)
+def test_tf32_is_deterministic_and_shard_independent(vlg, tc):
     g = Hh.load("ens_seed12_entropy")
     dec = make_decoders(vlg, g, 10)
     t = torch.linspace(0, 1, 2000, device="cuda")
     outs = []
     for _ in range(2):
         m = make_model(vlg, g)
-        e = vlg.optimize_splines(m, dec, t, 2, M=2, seed=5, curve_id0=40, precision="tf32")
+        e = vlg.optimize_splines(m, dec, t, 2, M=2, seed=5, curve_id0=40, precision=tc)
         outs.append((m.omega.clone(), e.clone()))
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
     sub = {k: (v[2:5] if k in ("a", "b", "omega_init") else v) for k, v in g.items()}
     m = make_model(vlg, sub)
-    e = vlg.optimize_splines(m, dec, t, 2, M=2, seed=5, curve_id0=42, precision="tf32")
+    e = vlg.optimize_splines(m, dec, t, 2, M=2, seed=5, curve_id0=42, precision=tc)
     assert torch.equal(m.omega, outs[0][0][2:5]) and torch.equal(e, outs[0][1][2:5])
 
 
@@ -382,7 +388,7 @@ def test_config5_shape_k64_npoly8_t256(vlg):
     assert np.abs(out["tf32"][1] - r["omega"]).max() < 0.25 * S * 1e-3 + 1e-6
 
 
-@pytest.mark.parametrize("prec,tol", [("fp32", 1e-3), ("tf32", 1e-3)])
+@pytest.mark.parametrize("prec,tol", [("fp32", 1e-3), ("tf32", 1e-3), ("f16", 1e-3)])
 def test_full_config1_1000_steps_final_lengths(vlg, prec, tol):
     """North-star statement: BASELINE config 1 at full length (45 curves, K=10, M=2, T=2000, 1000 Adam
     steps) against the reference's own fp64 run with the same counter-based draws

@@ -60,3 +60,22 @@ def test_3xtf32_is_fp32_grade(built_lib, N, K, mn):
     D, ref = run(N, K, mn, 1)
     err = (D - ref).abs().max().item() / ref.abs().max().item()
     assert err < 2e-5, err
+
+
+@pytest.mark.parametrize("N,K", [(128, 128), (64, 128), (128, 64), (16, 16)])
+def test_f16_mma_matches_matmul(built_lib, N, K):
+    """kind::f16: fp16 pairs in TMEM (even k in the low half), fp16 image img16[(k/8)*N + n][k%8]."""
+    from vlg_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(N + K)
+    B = torch.randn(N, K, generator=g)
+    A = torch.randn(128, K, generator=g)
+    img = B.half().reshape(N, K // 8, 8).permute(1, 0, 2).contiguous().cuda()
+    D = torch.zeros(128, N, device="cuda")
+    rc = lib.vlg_selftest_umma_f16(A.cuda().data_ptr(), img.data_ptr(), D.data_ptr(), N, K,
+                                   torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    torch.cuda.synchronize()
+    ref = A.half().double() @ B.half().double().T     # exact products of the rounded operands
+    err = (D.cpu().double() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 1e-5, err

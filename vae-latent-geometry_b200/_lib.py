@@ -41,6 +41,7 @@ SIGNATURES = {
 # test hooks declared in include/vlg_selftest.h
 SELFTEST_SIGNATURES = {
     "vlg_selftest_umma": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "vlg_selftest_umma_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
 }
 
 

@@ -87,7 +87,7 @@ int fill_params(vlg::StepParams* p, const void* packed, int K_active, int N, int
                 cudaStream_t stream) {
   if (!packed || N <= 0 || T < 2 || n_poly < 1 || M < 1 || K_active < 1) return VLG_ERR_INVALID_ARGUMENT;
   if (n_poly > vlg::MAX_NPOLY || M > vlg::MAX_M || K_active > 254) return VLG_ERR_UNSUPPORTED;
-  if (precision < VLG_PRECISION_FP32 || precision > VLG_PRECISION_TF32X3) return VLG_ERR_INVALID_ARGUMENT;
+  if (precision < VLG_PRECISION_FP32 || precision > VLG_PRECISION_F16) return VLG_ERR_INVALID_ARGUMENT;
   int K = 0, X = 0;
   int rc = lookup_packed(packed, &K, &X, stream);
   if (rc != VLG_OK) return rc;

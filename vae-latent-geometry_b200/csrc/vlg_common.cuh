@@ -25,11 +25,14 @@ constexpr int MAX_K = 255;      // decoder index travels as uint8; 255 = "none"
 //   W3      : [out 64][in 128]     fp32 (rows >= X are zero)
 //   tcgen05 B-operand images, canonical no-swizzle K-major layout img[k/4][n][k%4]
 //   (8x16B core matrices; SBO = 128 B between 8-row groups, LBO = N*16 B between k-chunks),
-//   values pre-rounded to TF32 (round-to-nearest); the *_LO images hold w - tf32(w):
+//   values pre-rounded to TF32 (round-to-nearest):
 //   W2_UMMA  : B[n=out][k=in]  = W2[out][in]   N=128 K=128   (h1 * W2^T)
 //   W3_UMMA  : B[n=out][k=in]  = W3[out][in]   N=64  K=128   (h2 * W3^T, rows >= X zero)
 //   W3T_UMMA : B[n=in][k=out]  = W3[out][in]   N=128 K=64    (dx  * W3)
 //   W2T_UMMA : B[n=in][k=out]  = W2[out][in]   N=128 K=128   (dh2 * W2)
+//   the same four matrices as fp16 images (round-to-nearest) for kind::f16,
+//   img16[k/8][n][k%8] (16-bit elements: a 16-byte core-matrix row holds 8 k; same SBO / LBO):
+//   W2_H, W3_H, W3T_H, W2T_H  (offsets below are in floats; an image of N x K halves takes N*K/2)
 // ---------------------------------------------------------------------------------------
 struct PackedHeader {
   uint32_t magic;    // 'VLG1'
@@ -53,11 +56,11 @@ constexpr int OFF_W2_UMMA = OFF_W3 + XP * H;
 constexpr int OFF_W3_UMMA = OFF_W2_UMMA + H * H;
 constexpr int OFF_W3T_UMMA = OFF_W3_UMMA + XP * H;
 constexpr int OFF_W2T_UMMA = OFF_W3T_UMMA + XP * H;
-constexpr int OFF_W2_LO = OFF_W2T_UMMA + H * H;
-constexpr int OFF_W3_LO = OFF_W2_LO + H * H;
-constexpr int OFF_W3T_LO = OFF_W3_LO + XP * H;
-constexpr int OFF_W2T_LO = OFF_W3T_LO + XP * H;
-constexpr int DEC_FLOATS = OFF_W2T_LO + H * H;
+constexpr int OFF_W2_H = OFF_W2T_UMMA + H * H;
+constexpr int OFF_W3_H = OFF_W2_H + H * H / 2;
+constexpr int OFF_W3T_H = OFF_W3_H + XP * H / 2;
+constexpr int OFF_W2T_H = OFF_W3T_H + XP * H / 2;
+constexpr int DEC_FLOATS = OFF_W2T_H + H * H / 2;
 static_assert(DEC_FLOATS % 64 == 0 && OFF_W2_UMMA % 4 == 0, "images must stay 16-byte aligned");
 
 __host__ __device__ inline const float* dec_ptr(const void* packed, int k) {

@@ -1,6 +1,8 @@
 // Weight repacking and the small forward-only helpers (disagreement field, spline
 // evaluation, least-squares spline fit).  None of these are hot; they exist so the
 // drop-in entry points never leave the GPU and never need a CPU fallback.
+#include <cuda_fp16.h>
+
 #include "vlg_common.cuh"
 #include "vlg_kernels.h"
 
@@ -47,9 +49,10 @@ __global__ void pack_kernel(const float* __restrict__ W1, const float* __restric
     const int ut = ((o >> 2) * H + in) * 4 + (o & 3);   // B[n=in][k=o]
     const float hi = tf32_rn(w);
     d[OFF_W2_UMMA + u] = hi;
-    d[OFF_W2_LO + u] = w - hi;
     d[OFF_W2T_UMMA + ut] = hi;
-    d[OFF_W2T_LO + ut] = w - hi;
+    const __half wh = __float2half_rn(w);
+    reinterpret_cast<__half*>(d + OFF_W2_H)[((in >> 3) * H + o) * 8 + (in & 7)] = wh;
+    reinterpret_cast<__half*>(d + OFF_W2T_H)[((o >> 3) * H + in) * 8 + (o & 7)] = wh;
   }
   for (int i = threadIdx.x; i < XP * H; i += blockDim.x) {
     const int o = i / H, in = i % H;  // W3[o][in], zero rows o >= X
@@ -60,9 +63,10 @@ __global__ void pack_kernel(const float* __restrict__ W1, const float* __restric
     const int ut = ((o >> 2) * H + in) * 4 + (o & 3);    // B[n=in][k=o], N = 128, K = 64
     const float hi = tf32_rn(w);
     d[OFF_W3_UMMA + u] = hi;
-    d[OFF_W3_LO + u] = w - hi;
     d[OFF_W3T_UMMA + ut] = hi;
-    d[OFF_W3T_LO + ut] = w - hi;
+    const __half wh = __float2half_rn(w);
+    reinterpret_cast<__half*>(d + OFF_W3_H)[((in >> 3) * XP + o) * 8 + (in & 7)] = wh;   // N = 64, K = 128
+    reinterpret_cast<__half*>(d + OFF_W3T_H)[((o >> 3) * H + in) * 8 + (o & 7)] = wh;    // N = 128, K = 64
   }
 }
 

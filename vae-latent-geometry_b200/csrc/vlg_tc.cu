@@ -33,6 +33,7 @@
 // right-end output x2 in an L2-resident workspace) -> one pass forms x2-x1 and the energy ->
 // backward items (input gradient only; layer-2 ReLU masks as bits in the workspace, layer-1
 // mask recomputed) -> dz per point -> d(omega).  Penalty gradient and Adam as in vlg_simt.cu.
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include "vlg_common.cuh"
@@ -72,18 +73,45 @@ struct OpInfo {
   int img_off;   // float offset of the B image inside the decoder record
   int nstages;   // 16 KB stages
   int n;         // MMA N
-  int kper;      // contraction length per stage
+  int nk;        // MMAs per stage (8 TMEM columns of A each: 8 tf32 or 16 fp16 contraction indices)
   int a_col;     // chain-relative TMEM column of A
   int d_col;     // chain-relative TMEM column of D
 };
+// kind::tf32: activations are fp32 words with TF32-rounded bits, one per TMEM column; an accumulator is
+// overwritten in place by the next layer's operand (X = columns 0..127 of the chain, Y = 128..255).
+// kind::f16 : activations are fp16 pairs, two per column, so an operand takes half the columns of the
+// accumulator it was computed from and cannot be written in place (another thread's accumulator
+// columns would be hit): operands always go to X[0:64], accumulators to Y or X[64:128].
+template <bool F16>
 __device__ __forceinline__ OpInfo op_info(int op) {
+  if (F16) {
+    switch (op) {
+      case 0: return {OFF_W2_H, 2, 128, 4, 0, 128};     // F2: D2(Y) = A1(X[0:64]) * W2^T
+      case 1: return {OFF_W3_H, 1, 64, 8, 0, 64};       // F3: D3(X[64:128]) = A2(X[0:64]) * W3^T
+      case 2: return {OFF_W3T_H, 1, 128, 4, 0, 128};    // B3: D4(Y) = G(X[0:32]) * W3
+      default: return {OFF_W2T_H, 2, 128, 4, 0, 128};   // B2: D5(Y) = A4(X[0:64]) * W2
+    }
+  }
   switch (op) {
-    case 0: return {OFF_W2_UMMA, 4, 128, 32, 0, 128};    // F2: D2(Y) = A1(X) * W2^T
-    case 1: return {OFF_W3_UMMA, 2, 64, 64, 128, 0};     // F3: D3(X[0:64]) = A2(Y) * W3^T
-    case 2: return {OFF_W3T_UMMA, 2, 128, 32, 0, 128};   // B3: D4(Y) = G(X[0:64]) * W3
-    default: return {OFF_W2T_UMMA, 4, 128, 32, 128, 0};  // B2: D5(X) = A4(Y) * W2
+    case 0: return {OFF_W2_UMMA, 4, 128, 4, 0, 128};    // F2: D2(Y) = A1(X) * W2^T
+    case 1: return {OFF_W3_UMMA, 2, 64, 8, 128, 0};     // F3: D3(X[0:64]) = A2(Y) * W3^T
+    case 2: return {OFF_W3T_UMMA, 2, 128, 4, 0, 128};   // B3: D4(Y) = G(X[0:64]) * W3
+    default: return {OFF_W2T_UMMA, 4, 128, 4, 128, 0};  // B2: D5(X) = A4(Y) * W2
   }
 }
+// two fp32 -> one fp16x2 word (round-to-nearest; lo half = first argument), optionally through relu
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t pack_relu_h2(float a, float b) {
+  const __half2 h = __hmax2(__floats2half2_rn(a, b), __float2half2_rn(0.f));
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+// Backward quantities (dE/dx and the hidden-layer gradients) are scaled by 2^6 before they are rounded to
+// fp16 and unscaled in fp32 when dz is accumulated: gradients of a converged curve are O(1e-2 .. 1e-5)
+// per element, fp16 loses precision below 6e-5.
+constexpr float F16_GRAD_SCALE = 64.f;
 
 // round-to-nearest to TF32 for finite values: the tensor core ignores the 13 low mantissa bits
 __device__ __forceinline__ uint32_t tf32_round_bits(uint32_t b) { return b + 0x1000u; }
@@ -194,7 +222,7 @@ static int tc_stages(int W, int K, int M) {
   return int(nst);
 }
 
-template <bool GRAD>
+template <bool GRAD, bool F16>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, int nst, int W) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -253,7 +281,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
           for (int i = c; i < nit; i += 2) {
             const int k = ctl->item[i] & 0xFF;
             for (int o = 0; o < 2; ++o) {
-              const OpInfo oi = op_info(phase * 2 + o);
+              const OpInfo oi = op_info<F16>(phase * 2 + o);
               const char* src = reinterpret_cast<const char*>(dec_ptr(p.packed, k) + oi.img_off);
               for (int st = 0; st < oi.nstages; ++st) {
                 mbar_wait(&emptyc[slot], ph ^ 1);
@@ -305,8 +333,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
           tc_fence_after();
           // op order inside a window: F2 F3 per item, then B3 B2 per item
           const int optype = (opi[c] < 2 * nitc[c]) ? (opi[c] & 1) : 2 + ((opi[c] - 2 * nitc[c]) & 1);
-          const OpInfo oi = op_info(optype);
-          const uint32_t idesc = umma_idesc_tf32(oi.n, 0);
+          const OpInfo oi = op_info<F16>(optype);
+          const uint32_t idesc = F16 ? umma_idesc_f16(oi.n) : umma_idesc_tf32(oi.n, 0);
           const uint32_t chain = tmem + uint32_t(c) * 256u;
           uint64_t* fullc = full + c * MAX_STAGES;
           uint64_t* emptyc = empty + c * MAX_STAGES;
@@ -315,14 +343,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
             if (!mbar_test(&fullc[slot[c]], ph[c])) { STAT_T0(); mbar_wait(&fullc[slot[c]], ph[c]); STAT_ADD(w_full); }
             tc_fence_after();
             const uint32_t sbase = smem_u32(ringc + slot[c] * STAGE_BYTES);
-            const int nk = oi.kper / 8;
+            const int nk = oi.nk;
             {
               STAT_T0();
               for (int ks = 0; ks < nk; ++ks) {
                 const uint64_t desc =
                     umma_smem_desc(sbase + uint32_t(ks) * 2u * uint32_t(oi.n) * 16u, uint32_t(oi.n) * 16u, 128u);
-                umma_tf32_ts_elect(chain + oi.d_col, chain + oi.a_col + uint32_t(st * oi.kper + ks * 8), desc, idesc,
-                                   (st | ks) ? 1u : 0u, leader);
+                const uint32_t a_addr = chain + oi.a_col + uint32_t((st * nk + ks) * 8);
+                if (F16)
+                  umma_f16_ts_elect(chain + oi.d_col, a_addr, desc, idesc, (st | ks) ? 1u : 0u, leader);
+                else
+                  umma_tf32_ts_elect(chain + oi.d_col, a_addr, desc, idesc, (st | ks) ? 1u : 0u, leader);
               }
               umma_commit_elect(&emptyc[slot[c]], leader);
               STAT_ADD(w_issue);
@@ -503,8 +534,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
             swsel ^= 1;
             const float2 z = s.zs[pt];
             const float2 zx2 = make_float2(z.x, z.x), zy2 = make_float2(z.y, z.y);
-            // layer 1 (CUDA cores, fp32) -> A1 in X[col0 : col0+64]
-            if (wact) {
+            // layer 1 (CUDA cores, fp32) -> A1 in X[col0 : col0+64]  (fp16: pairs in X[32 half : +32])
+            if (F16) {
+              if (wact) {
+                uint32_t v[32];
+#pragma unroll
+                for (int j = 0; j < 64; j += 4) {
+                  const int c = col0 + j;
+                  const float4 wx = *reinterpret_cast<const float4*>(sw + OFF_W1X + c);
+                  const float4 wy = *reinterpret_cast<const float4*>(sw + OFF_W1Y + c);
+                  const float4 bb = *reinterpret_cast<const float4*>(sw + OFF_B1 + c);
+                  const float2 h0 = __ffma2_rn(make_float2(wy.x, wy.y), zy2,
+                                               __ffma2_rn(make_float2(wx.x, wx.y), zx2, make_float2(bb.x, bb.y)));
+                  const float2 h1 = __ffma2_rn(make_float2(wy.z, wy.w), zy2,
+                                               __ffma2_rn(make_float2(wx.z, wx.w), zx2, make_float2(bb.z, bb.w)));
+                  v[j >> 1] = pack_relu_h2(h0.x, h0.y);
+                  v[(j >> 1) + 1] = pack_relu_h2(h1.x, h1.y);
+                }
+                tmem_st32(colX + half * 32, v);
+              }
+            } else if (wact) {
 #pragma unroll
               for (int c0 = 0; c0 < 64; c0 += 32) {
                 uint32_t v[32];
@@ -553,11 +602,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                 if (q0f.y > 0.f) bits1 |= 2u << j;
                 if (q1f.x > 0.f) bits1 |= 4u << j;
                 if (q1f.y > 0.f) bits1 |= 8u << j;
-                v0[j] = relu_tf32(p0.x); v0[j + 1] = relu_tf32(p0.y); v0[j + 2] = relu_tf32(p1.x); v0[j + 3] = relu_tf32(p1.y);
-                v1[j] = relu_tf32(q0f.x); v1[j + 1] = relu_tf32(q0f.y); v1[j + 2] = relu_tf32(q1f.x); v1[j + 3] = relu_tf32(q1f.y);
+                if (F16) {
+                  // v0[0:16] <- pairs of hidden units col0 .. col0+31, v0[16:32] <- col0+32 .. col0+63 (v1 is dead after this)
+                  const uint32_t a0 = pack_relu_h2(p0.x, p0.y), a1 = pack_relu_h2(p1.x, p1.y);
+                  const uint32_t c0 = pack_relu_h2(q0f.x, q0f.y), c1 = pack_relu_h2(q1f.x, q1f.y);
+                  v1[j >> 1] = c0; v1[(j >> 1) + 1] = c1;   // j/2 <= j: slots already consumed
+                  v0[j >> 1] = a0; v0[(j >> 1) + 1] = a1;
+                } else {
+                  v0[j] = relu_tf32(p0.x); v0[j + 1] = relu_tf32(p0.y); v0[j + 2] = relu_tf32(p1.x); v0[j + 3] = relu_tf32(p1.y);
+                  v1[j] = relu_tf32(q0f.x); v1[j + 1] = relu_tf32(q0f.y); v1[j + 2] = relu_tf32(q1f.x); v1[j + 3] = relu_tf32(q1f.y);
+                }
               }
-              tmem_st32(colY + col0, v0);
-              tmem_st32(colY + col0 + 32, v1);
+              if (F16) {
+                tmem_st16(colX + half * 32, reinterpret_cast<uint32_t(&)[16]>(v0));
+                tmem_st16(colX + half * 32 + 16, reinterpret_cast<uint32_t(&)[16]>(v1));
+              } else {
+                tmem_st32(colY + col0, v0);
+                tmem_st32(colY + col0 + 32, v1);
+              }
               if (GRAD && active) *reinterpret_cast<uint2*>(maskws + (it * 128 + row) * 4 + half * 2) = make_uint2(bits0, bits1);
             }
             tmem_wait_st();
@@ -569,7 +631,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
             tc_fence_after();
             if (wact) {
               uint32_t xv[32];
-              tmem_ld32_sync(colX + xc0, xv);
+              tmem_ld32_sync(colX + (F16 ? 64 : 0) + xc0, xv);
               float x[32];
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
@@ -684,10 +746,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                       }
                   }
                 }
-                uint32_t v[32];
+                if (F16) {
+                  uint32_t v[16];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = tf32_round_bits(__float_as_uint(coefm * g[j]));
-                tmem_st32(colX + xc0, v);
+                  for (int j = 0; j < 16; ++j) v[j] = pack_h2((coefm * F16_GRAD_SCALE) * g[2 * j], (coefm * F16_GRAD_SCALE) * g[2 * j + 1]);
+                  tmem_st16(colX + half * 16, v);
+                } else {
+                  uint32_t v[32];
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) v[j] = tf32_round_bits(__float_as_uint(coefm * g[j]));
+                  tmem_st32(colX + xc0, v);
+                }
               }
               tmem_wait_st();
               tc_fence_before();
@@ -699,13 +768,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
               if (wact) {
                 uint32_t v0[32], v1[32];
                 tmem_ld32x2_sync(colY + col0, colY + col0 + 32, v0, v1);
+                if (F16) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                  v0[j] = ((bits.x >> j) & 1u) ? tf32_round_bits(v0[j]) : 0u;
-                  v1[j] = ((bits.y >> j) & 1u) ? tf32_round_bits(v1[j]) : 0u;
+                  for (int j = 0; j < 32; j += 2) {
+                    const float a0 = ((bits.x >> j) & 1u) ? __uint_as_float(v0[j]) : 0.f;
+                    const float a1 = ((bits.x >> (j + 1)) & 1u) ? __uint_as_float(v0[j + 1]) : 0.f;
+                    const float c0 = ((bits.y >> j) & 1u) ? __uint_as_float(v1[j]) : 0.f;
+                    const float c1 = ((bits.y >> (j + 1)) & 1u) ? __uint_as_float(v1[j + 1]) : 0.f;
+                    v0[j >> 1] = pack_h2(a0, a1);   // j/2 <= j: slots already consumed
+                    v1[j >> 1] = pack_h2(c0, c1);
+                  }
+                  tmem_st16(colX + half * 32, reinterpret_cast<uint32_t(&)[16]>(v0));
+                  tmem_st16(colX + half * 32 + 16, reinterpret_cast<uint32_t(&)[16]>(v1));
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) {
+                    v0[j] = ((bits.x >> j) & 1u) ? tf32_round_bits(v0[j]) : 0u;
+                    v1[j] = ((bits.y >> j) & 1u) ? tf32_round_bits(v1[j]) : 0u;
+                  }
+                  tmem_st32(colY + col0, v0);
+                  tmem_st32(colY + col0 + 32, v1);
                 }
-                tmem_st32(colY + col0, v0);
-                tmem_st32(colY + col0 + 32, v1);
               }
               tmem_wait_st();
               tc_fence_before();
@@ -716,7 +799,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
               tc_fence_after();
               if (wact) {
                 uint32_t v0[32], v1[32];
-                tmem_ld32x2_sync(colX + col0, colX + col0 + 32, v0, v1);
+                tmem_ld32x2_sync((F16 ? colY : colX) + col0, (F16 ? colY : colX) + col0 + 32, v0, v1);
                 float2 ax = make_float2(0.f, 0.f), ay = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int j = 0; j < 64; j += 2) {
@@ -736,8 +819,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                 if (active) {
                   float2* dzp = &s.dzs[(chain_id * 2 + half) * W + pt];
                   float2 acc = *dzp;
-                  acc.x += ax.x + ax.y;
-                  acc.y += ay.x + ay.y;
+                  constexpr float unscale = F16 ? 1.f / F16_GRAD_SCALE : 1.f;
+                  acc.x += (ax.x + ax.y) * unscale;
+                  acc.y += (ay.x + ay.y) * unscale;
                   *dzp = acc;
                 }
               }
@@ -894,7 +978,8 @@ extern "C" int vlg_debug_tc_stats(long long* host_out, int n) {
 #endif
 
 cudaError_t launch_tc(const StepParams& p, bool grad, cudaStream_t stream) {
-  if (p.precision != 1) return cudaErrorNotSupported;  // 3xTF32 not built yet
+  if (p.precision != 1 && p.precision != 3) return cudaErrorNotSupported;  // 3xTF32 not built
+  const bool f16 = p.precision == 3;
   if (p.M > TC_MAX_M || p.K > TC_MAX_K) return cudaErrorNotSupported;
   const int W = tc_window_points(p.T, p.K, p.M);
   if (W < 2) return cudaErrorNotSupported;
@@ -908,16 +993,14 @@ cudaError_t launch_tc(const StepParams& p, bool grad, cudaStream_t stream) {
   q.unit_steps = (q.steps + nchunks - 1) / nchunks;
   cudaError_t e = cudaMemsetAsync(p.workspace, 0, tc_queue_words(p.N) * 4, stream);
   if (e != cudaSuccess) return e;
-  if (grad) {
-    e = cudaFuncSetAttribute(tc_curve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    if (e != cudaSuccess) return e;
-    tc_curve_kernel<true><<<grid, TC_THREADS, smem, stream>>>(q, nst, W);
-  } else {
-    e = cudaFuncSetAttribute(tc_curve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    if (e != cudaSuccess) return e;
-    tc_curve_kernel<false><<<grid, TC_THREADS, smem, stream>>>(q, nst, W);
-  }
-  return cudaGetLastError();
+  auto launch = [&](auto kernel) -> cudaError_t {
+    cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (err != cudaSuccess) return err;
+    kernel<<<grid, TC_THREADS, smem, stream>>>(q, nst, W);
+    return cudaGetLastError();
+  };
+  if (grad) return f16 ? launch(tc_curve_kernel<true, true>) : launch(tc_curve_kernel<true, false>);
+  return f16 ? launch(tc_curve_kernel<false, true>) : launch(tc_curve_kernel<false, false>);
 }
 
 }  // namespace vlg

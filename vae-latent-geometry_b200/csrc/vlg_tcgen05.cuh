@@ -140,6 +140,13 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32(int N, int b_mn_major) {
          | (uint32_t(128 >> 4) << 24);   // M
 }
 
+// Instruction descriptor for kind::f16 with fp16 A and B (format code 0), fp32 accumulate, M = 128.
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int N) {
+  return (1u << 4)                      // D format F32
+         | (uint32_t(N >> 3) << 17)     // N
+         | (uint32_t(128 >> 4) << 24);  // M
+}
+
 // D[tmem] (+)= A[tmem] * B[smem]; issued by ONE thread.
 __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
                                              uint32_t accumulate) {
@@ -172,6 +179,17 @@ __device__ __forceinline__ void umma_tf32_ts_elect(uint32_t d_tmem, uint32_t a_t
       "setp.ne.b32 p, %4, 0;\n\t"
       "setp.ne.b32 q, %5, 0;\n\t"
       "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(leader)
+      : "memory");
+}
+// kind::f16: A holds two 16-bit values per TMEM column (K = 16 per instruction = 8 columns)
+__device__ __forceinline__ void umma_f16_ts_elect(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                                  uint32_t accumulate, uint32_t leader) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
       "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(leader)
       : "memory");
 }

@@ -1,6 +1,8 @@
 // Unit-test kernel for the tcgen05 building blocks (see include/vlg_selftest.h).
 #include "../../include/vlg.h"
 #include "../../include/vlg_selftest.h"
+#include <cuda_fp16.h>
+
 #include "vlg_common.cuh"
 #include "vlg_tcgen05.cuh"
 
@@ -221,5 +223,78 @@ extern "C" int vlg_selftest_mma_rate(int N, int iters, int lbo, int sbo, int cta
   cudaError_t e = cudaFuncSetAttribute(vlg::mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
   if (e != cudaSuccess) return VLG_ERR_CUDA;
   vlg::mma_rate_kernel<<<ctas, 384, smem, static_cast<cudaStream_t>(stream)>>>(N, iters, lbo, sbo, mode, out);
+  return cudaGetLastError() == cudaSuccess ? VLG_OK : VLG_ERR_CUDA;
+}
+
+// ---- kind::f16 building block: A[128,K] fp32 -> fp16 pairs in TMEM (two k per column, even k in the
+// low half), B = fp16 image img16[k/8][n][k%8] bulk-copied to shared memory, fp32 accumulate ----
+namespace vlg {
+namespace {
+__global__ void __launch_bounds__(128) umma_f16_selftest_kernel(const float* __restrict__ A, const void* __restrict__ Bimg,
+                                                                float* __restrict__ D, int N, int K) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bar_b, bar_mma;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) {
+    tc::mbar_init(&bar_b, 1);
+    tc::mbar_init(&bar_mma, 1);
+    tc::fence_mbar_init();
+  }
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t lane_base = uint32_t(warp * 32) << 16;
+  const uint32_t colA = 0, colD = 256;
+  if (tid == 0) {
+    const uint32_t bytes = uint32_t(N) * K * 2;
+    tc::mbar_expect_tx(&bar_b, bytes);
+    tc::bulk_g2s(smem, Bimg, bytes, &bar_b);
+  }
+  for (int c0 = 0; c0 < K / 2; c0 += 16) {
+    uint32_t v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const __half2 h = __floats2half2_rn(A[size_t(tid) * K + 2 * (c0 + j)], A[size_t(tid) * K + 2 * (c0 + j) + 1]);
+      v[j] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    tc::tmem_st16(tmem + lane_base + colA + c0, v);
+  }
+  tc::tmem_wait_st();
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    const uint32_t leader = tc::elect_one();
+    tc::tc_fence_after();
+    tc::mbar_wait(&bar_b, 0);
+    const uint32_t idesc = tc::umma_idesc_f16(N);
+    for (int ks = 0; ks < K / 16; ++ks) {
+      const uint64_t desc = tc::umma_smem_desc(tc::smem_u32(smem) + uint32_t(ks) * 2u * uint32_t(N) * 16u, uint32_t(N) * 16u, 128u);
+      tc::umma_f16_ts_elect(tmem + colD, tmem + colA + uint32_t(ks) * 8u, desc, idesc, ks ? 1u : 0u, leader);
+    }
+    tc::umma_commit_elect(&bar_mma, leader);
+  }
+  tc::mbar_wait(&bar_mma, 0);
+  tc::tc_fence_after();
+  for (int c0 = 0; c0 < N; c0 += 16) {
+    uint32_t v[16];
+    tc::tmem_ld16(tmem + lane_base + colD + c0, v);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) D[size_t(tid) * N + c0 + j] = __uint_as_float(v[j]);
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+}  // namespace
+}  // namespace vlg
+
+extern "C" int vlg_selftest_umma_f16(const float* A, const void* Bimg16, float* D, int N, int K, void* stream) {
+  if (!A || !Bimg16 || !D) return VLG_ERR_INVALID_ARGUMENT;
+  if (N % 16 || K % 16 || N < 16 || N > 128 || K < 16 || K > 128) return VLG_ERR_UNSUPPORTED;
+  const size_t smem = size_t(N) * K * 2;
+  vlg::umma_f16_selftest_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(A, Bimg16, D, N, K);
   return cudaGetLastError() == cudaSuccess ? VLG_OK : VLG_ERR_CUDA;
 }
