@@ -12,7 +12,7 @@ basis, _ = vlg_b200.construct_nullspace_basis(4)
 m = vlg_b200.GeodesicSplineBatch(a.to(dev), b.to(dev), basis.to(dev), om.to(dev), 4)
 t = torch.linspace(0, 1, 2000, device=dev)
 for _ in range(2):
-    vlg_b200.optimize_splines(m, dec, t, 1, M=2, seed=0, precision="tf32")
+    vlg_b200.optimize_splines(m, dec, t, 1, M=2, seed=0, precision=(sys.argv[2] if len(sys.argv) > 2 else "tf32"))
 torch.cuda.synchronize()
 lib = _lib.load()
 out = (ctypes.c_longlong * (nc * 8))()
@@ -25,6 +25,8 @@ for i, nm in enumerate(names):
         print(f"{nm:22s} mean {st[:, i].mean():12.0f} cycles  ({100 * st[:, i].mean() / st[:, 3].mean():5.1f}% of mma total)")
 
 
+if not hasattr(lib, "vlg_debug_tc_phase"):
+    sys.exit(0)
 ph = (ctypes.c_longlong * (nc * 48))()
 lib.vlg_debug_tc_phase.argtypes = [ctypes.c_void_p, ctypes.c_int]
 assert lib.vlg_debug_tc_phase(ph, nc) == 0

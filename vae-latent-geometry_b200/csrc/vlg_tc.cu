@@ -661,9 +661,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
           named_bar(3, EPI_THREADS);
 
           // ======================= x2 - x1 and the energy =======================
-          // 16 lanes per (m, segment) entry, one 16-byte piece each, so the L2 reads of x2 are
-          // coalesced 208-byte rows; six entries per lane are in flight before the first is used.
-          {
+          if (GRAD) {
+            // The valid rows of one MC sample are contiguous in both buffers: a flat, fully coalesced pass
+            // over 16-byte pieces (x2 from L2, x1 from shared memory, the difference back in place), four
+            // independent pieces per thread in flight.  The energy is the plain sum of squares, in a fixed
+            // order (deterministic).
+            float e = 0.f;
+            const int n4 = nseg * (XD_STRIDE / 4);
+            for (int m = 0; m < M; ++m) {
+              const float4* x2 = reinterpret_cast<const float4*>(X2 + m * W * XD_STRIDE);
+              float4* x1 = reinterpret_cast<float4*>(X1 + m * W * XD_STRIDE);
+              for (int i0 = t512; i0 < n4; i0 += 4 * EPI_THREADS) {
+                float4 v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const int i = i0 + j * EPI_THREADS;
+                  v[j] = i < n4 ? __ldcg(x2 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const int i = i0 + j * EPI_THREADS;
+                  if (i < n4) {
+                    const float4 u = x1[i];
+                    const float4 a = make_float4(v[j].x - u.x, v[j].y - u.y, v[j].z - u.z, v[j].w - u.w);
+                    x1[i] = a;
+                    e = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(a.z, a.z, fmaf(a.w, a.w, e))));
+                  }
+                }
+              }
+            }
+            e = warp_sum(e);
+            if (lane == 0) s.red[320 + ew] = e;
+          } else {
+            // forward-only kernel (also reports the polyline length, a sum of per-segment norms): 16 lanes
+            // per (m, segment) entry, one 16-byte piece each; six entries per lane in flight.
             float e = 0.f, l = 0.f;
             const int sub = lane & 15;
             constexpr int NV = XD_STRIDE / 4;   // 13 float4 per row
