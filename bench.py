@@ -2,7 +2,7 @@
 """Benchmark of the geodesic curve-energy hot path (BASELINE.json metric: spline-steps/sec,
 8778-pair 10-decoder eVAE energy optimisation).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--precision tf32|fp32]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--precision f16|tf32|fp32]
 
 A "step" is one Adam step of EVERY curve of the workload (= n_curves spline-steps): spline
 evaluation, all-decoder forward + input-gradient backward, MC pair energy, Adam -- one pass of
@@ -39,6 +39,12 @@ K_DEC = 10
 M_MC = 2
 FLOP_PER_POINT_DECODER = 92160  # fwd + input-grad bwd of 2->128->128->50
 METRIC = "spline-steps/sec, 8778-pair 10-decoder eVAE energy opt"
+# arithmetic of the two 128-wide decoder layers (layer 1, the energy, the spline and Adam are fp32 everywhere)
+PRECISION_NOTE = {
+    "f16": "f16: tcgen05 kind::f16, fp16 operands (11-bit significand, as TF32), fp32 accumulate; <=1e-3 rel. on lengths",
+    "tf32": "tf32: tcgen05 kind::tf32, fp32 accumulate; <=1e-3 rel. on lengths",
+    "fp32": "fp32: CUDA-core FFMA; <=1e-4 rel. per-step energy",
+}
 
 
 def synthetic_workload(n_curves, seed=0):
@@ -289,16 +295,16 @@ def run_gpu_arm(args):
         achieved = flops_local / (kernel_ms * 1e-3) / 1e12
         traffic = None
         tf = ROOT / "profiles" / "r01_traffic.json"
-        if tf.exists() and args.precision == "tf32":
+        if tf.exists() and args.precision in json.loads(tf.read_text()):
             # DRAM bytes per launch, scaled from the committed ncu capture of the same kernel
-            per = json.loads(tf.read_text())["dram_bytes_per_spline_step"]
+            per = json.loads(tf.read_text())[args.precision]["dram_bytes_per_spline_step"]
             traffic = per * n_local * args.steps / max(1, len(kernel_events))
         line = {
             "metric": METRIC, "value": value, "unit": "spline-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None,
-            "dtype": "tf32" if args.precision == "tf32" else "f32", "data": "synthetic",
-            "config": dict(workload_config(weights, world, "gpu"), precision=args.precision,
+            "dtype": {"f16": "f16", "tf32": "tf32", "fp32": "f32"}[args.precision], "data": "synthetic",
+            "config": dict(workload_config(weights, world, "gpu"), precision=PRECISION_NOTE[args.precision],
                            steps_per_launch=chunk),
             "clocks": clocks,
             "e2e": {"value": spline_steps / (ms_e2e * 1e-3), "unit": "spline-steps/s",
@@ -307,7 +313,8 @@ def run_gpu_arm(args):
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "tc_curve_kernel<true>" if args.precision == "tf32" else "simt_curve_kernel<true>",
+                         "kernel": {"f16": "tc_curve_kernel<true, true>", "tf32": "tc_curve_kernel<true, false>",
+                                    "fp32": "simt_curve_kernel<true>"}[args.precision],
                          "flop_per_spline_step": T_POINTS * K_DEC * FLOP_PER_POINT_DECODER,
                          "kernel_ms_per_step": kernel_ms / args.steps},
         }
@@ -327,7 +334,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="vlg", choices=["vlg", "reference"])
-    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
+    ap.add_argument("--precision", default="f16", choices=["f16", "tf32", "fp32"])
     ap.add_argument("--chunk", type=int, default=50, help="Adam steps per kernel launch")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
