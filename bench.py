@@ -263,16 +263,21 @@ def run_gpu_arm(args):
     h_out_om = torch.empty_like(h_om).pin_memory()
     h_out_e = torch.empty(n_local, dtype=torch.float32).pin_memory()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    done = 0
-    while done < args.steps:
-        ns = min(chunk, args.steps - done)
+
+    def e2e_call(ns):
         m2 = vlg_b200.GeodesicSplineBatch(h_a.to(dev, non_blocking=True), h_b.to(dev, non_blocking=True), basis,
                                           h_om.to(dev, non_blocking=True), N_POLY)
         en = vlg_b200.optimize_splines(m2, dec, t, ns, M=M_MC, seed=0, curve_id0=lo, precision=args.precision)
         h_out_om.copy_(m2.omega, non_blocking=True)
         h_out_e.copy_(en, non_blocking=True)
+
+    e2e_call(1)   # untimed warm-up of this path (first pinned H2D + allocator growth cost ~90 ms once)
+    barrier()
+    e0.record()
+    done = 0
+    while done < args.steps:
+        ns = min(chunk, args.steps - done)
+        e2e_call(ns)
         done += ns
     e1.record()
     barrier()

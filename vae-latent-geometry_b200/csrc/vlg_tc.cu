@@ -185,35 +185,53 @@ struct TcSmem {
 constexpr int CTL_FLOATS = (2 * sizeof(WinCtl) + 3) / 4;
 constexpr int BAR_WORDS = 2 * (4 * MAX_STAGES + 5);
 
+// Fixed-size pieces first, at compile-time offsets from the start of dynamic shared memory (their
+// addresses fold into immediates -- the epilogue code is short of registers), then the window-sized
+// arrays, then the weight rings.
+constexpr int FIX_SW = 0;                                   // 4 x 576
+constexpr int FIX_COEF = FIX_SW + 4 * 576;                  // 64
+constexpr int FIX_BASIS = FIX_COEF + 64;                    // 4 * MAX_NPOLY * MAX_KB
+constexpr int FIX_OM = FIX_BASIS + 4 * MAX_NPOLY * MAX_KB;  // 3 * 2 * MAX_KB + 2
+constexpr int FIX_GACC = FIX_OM + 3 * 2 * MAX_KB + 2;       // 2 * MAX_KB + 2
+constexpr int FIX_RED = FIX_GACC + 2 * MAX_KB + 2;          // 352
+constexpr int FIX_BARS = FIX_RED + 352;                     // BAR_WORDS (8-byte aligned)
+constexpr int FIX_TMEM = FIX_BARS + BAR_WORDS;              // 4
+constexpr int FIX_CTL = FIX_TMEM + 4;                       // CTL_FLOATS
+constexpr int FIX_CNT = FIX_CTL + CTL_FLOATS;               // TC_MAX_K
+constexpr int FIX_FLOATS = (FIX_CNT + TC_MAX_K + 3) / 4 * 4;  // XD starts 16-byte aligned
+static_assert(FIX_BARS % 2 == 0, "mbarriers need 8-byte alignment");
+
 __device__ __forceinline__ TcSmem tc_carve(unsigned char* base, int W, int K, int M, int nst) {
   TcSmem s;
-  s.ring = base;
-  float* f = reinterpret_cast<float*>(base + 2 * nst * STAGE_BYTES);
+  float* f = reinterpret_cast<float*>(base);
+  s.sw = f + FIX_SW;
+  s.coef = f + FIX_COEF;
+  s.basis = f + FIX_BASIS;
+  s.om = f + FIX_OM;
+  s.gacc = f + FIX_GACC;
+  s.red = f + FIX_RED;
+  s.bars = reinterpret_cast<uint64_t*>(f + FIX_BARS);
+  s.tmem_base = reinterpret_cast<uint32_t*>(f + FIX_TMEM);
+  s.ctl = reinterpret_cast<WinCtl*>(f + FIX_CTL);
+  s.cnt = reinterpret_cast<int*>(f + FIX_CNT);
+  f += FIX_FLOATS;
   s.XD = f; f += M * W * XD_STRIDE;
-  s.sw = f; f += 4 * 576;
   s.zs = reinterpret_cast<float2*>(f); f += 2 * W;
   s.dzs = reinterpret_cast<float2*>(f); f += 2 * 4 * W;
-  s.coef = f; f += 64;
-  s.basis = f; f += 4 * MAX_NPOLY * MAX_KB;
-  s.om = f; f += 3 * 2 * MAX_KB + 2;
-  s.gacc = f; f += 2 * MAX_KB + 2;
-  s.red = f; f += 352;
-  s.bars = reinterpret_cast<uint64_t*>(f); f += BAR_WORDS;
-  s.tmem_base = reinterpret_cast<uint32_t*>(f); f += 4;
-  s.ctl = reinterpret_cast<WinCtl*>(f); f += CTL_FLOATS;
-  s.cnt = reinterpret_cast<int*>(f); f += TC_MAX_K;
-  s.sel = reinterpret_cast<uint8_t*>(f); f += TC_MAX_M * 2 * W / 4;
+  s.sel = reinterpret_cast<uint8_t*>(f); f += TC_MAX_M * 2 * W / 4 + 1;
   s.rows = reinterpret_cast<uint16_t*>(f);
-  (void)K;
+  const size_t ring_off = (size_t(reinterpret_cast<unsigned char*>(f) - base) + size_t(K) * W * 2 + 127) / 128 * 128;
+  s.ring = base + ring_off;
+  (void)nst;
   return s;
 }
 
 }  // namespace
 
 static size_t tc_smem_fixed_bytes(int W, int K, int M) {
-  size_t fl = size_t(M) * W * XD_STRIDE + 4 * 576 + 2 * size_t(W) + 2 * 4 * size_t(W) + 64 + 4 * MAX_NPOLY * MAX_KB + (3 * 2 * MAX_KB + 2) +
-              (2 * MAX_KB + 2) + 352 + BAR_WORDS + 4 + CTL_FLOATS + TC_MAX_K + TC_MAX_M * 2 * size_t(W) / 4;
-  return fl * 4 + size_t(K) * W * 2;
+  // everything but the weight rings, in the order of tc_carve (+ alignment slack before the rings)
+  size_t fl = size_t(FIX_FLOATS) + size_t(M) * W * XD_STRIDE + 2 * size_t(W) + 2 * 4 * size_t(W) + TC_MAX_M * 2 * size_t(W) / 4 + 1;
+  return (fl * 4 + size_t(K) * W * 2 + 127) / 128 * 128;
 }
 static int tc_stages(int W, int K, int M) {
   const long budget = 232448 - long(tc_smem_fixed_bytes(W, K, M));
@@ -583,44 +601,38 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
             ph_acc ^= 1;
             tc_fence_after();
             if (wact) {
-              uint32_t v0[32], v1[32];
-              tmem_ld32x2_sync(colY + col0, colY + col0 + 32, v0, v1);
-              uint32_t bits0 = 0, bits1 = 0;
+              // two passes of 32 columns: one live 32-register tile instead of two (no spills)
+              uint32_t bits[2];
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 b0 = *reinterpret_cast<const float4*>(sw + OFF_B2 + col0 + j);
-                const float4 b1 = *reinterpret_cast<const float4*>(sw + OFF_B2 + col0 + 32 + j);
-                const float2 p0 = __fadd2_rn(make_float2(__uint_as_float(v0[j]), __uint_as_float(v0[j + 1])), make_float2(b0.x, b0.y));
-                const float2 p1 = __fadd2_rn(make_float2(__uint_as_float(v0[j + 2]), __uint_as_float(v0[j + 3])), make_float2(b0.z, b0.w));
-                const float2 q0f = __fadd2_rn(make_float2(__uint_as_float(v1[j]), __uint_as_float(v1[j + 1])), make_float2(b1.x, b1.y));
-                const float2 q1f = __fadd2_rn(make_float2(__uint_as_float(v1[j + 2]), __uint_as_float(v1[j + 3])), make_float2(b1.z, b1.w));
-                if (p0.x > 0.f) bits0 |= 1u << j;
-                if (p0.y > 0.f) bits0 |= 2u << j;
-                if (p1.x > 0.f) bits0 |= 4u << j;
-                if (p1.y > 0.f) bits0 |= 8u << j;
-                if (q0f.x > 0.f) bits1 |= 1u << j;
-                if (q0f.y > 0.f) bits1 |= 2u << j;
-                if (q1f.x > 0.f) bits1 |= 4u << j;
-                if (q1f.y > 0.f) bits1 |= 8u << j;
-                if (F16) {
-                  // v0[0:16] <- pairs of hidden units col0 .. col0+31, v0[16:32] <- col0+32 .. col0+63 (v1 is dead after this)
-                  const uint32_t a0 = pack_relu_h2(p0.x, p0.y), a1 = pack_relu_h2(p1.x, p1.y);
-                  const uint32_t c0 = pack_relu_h2(q0f.x, q0f.y), c1 = pack_relu_h2(q1f.x, q1f.y);
-                  v1[j >> 1] = c0; v1[(j >> 1) + 1] = c1;   // j/2 <= j: slots already consumed
-                  v0[j >> 1] = a0; v0[(j >> 1) + 1] = a1;
-                } else {
-                  v0[j] = relu_tf32(p0.x); v0[j + 1] = relu_tf32(p0.y); v0[j + 2] = relu_tf32(p1.x); v0[j + 3] = relu_tf32(p1.y);
-                  v1[j] = relu_tf32(q0f.x); v1[j + 1] = relu_tf32(q0f.y); v1[j + 2] = relu_tf32(q1f.x); v1[j + 3] = relu_tf32(q1f.y);
+              for (int hh = 0; hh < 2; ++hh) {
+                uint32_t v[32];
+                tmem_ld32_sync(colY + col0 + 32 * hh, v);
+                uint32_t bb = 0;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  const float4 b0 = *reinterpret_cast<const float4*>(sw + OFF_B2 + col0 + 32 * hh + j);
+                  const float2 p0 = __fadd2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), make_float2(b0.x, b0.y));
+                  const float2 p1 = __fadd2_rn(make_float2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])), make_float2(b0.z, b0.w));
+                  if (p0.x > 0.f) bb |= 1u << j;
+                  if (p0.y > 0.f) bb |= 2u << j;
+                  if (p1.x > 0.f) bb |= 4u << j;
+                  if (p1.y > 0.f) bb |= 8u << j;
+                  if (F16) {
+                    // pairs go to v[0:16] (slots j/2, j/2+1 <= j were consumed already)
+                    const uint32_t a0 = pack_relu_h2(p0.x, p0.y), a1 = pack_relu_h2(p1.x, p1.y);
+                    v[j >> 1] = a0;
+                    v[(j >> 1) + 1] = a1;
+                  } else {
+                    v[j] = relu_tf32(p0.x); v[j + 1] = relu_tf32(p0.y); v[j + 2] = relu_tf32(p1.x); v[j + 3] = relu_tf32(p1.y);
+                  }
                 }
+                bits[hh] = bb;
+                if (F16)
+                  tmem_st16(colX + half * 32 + 16 * hh, reinterpret_cast<uint32_t(&)[16]>(v));
+                else
+                  tmem_st32(colY + col0 + 32 * hh, v);
               }
-              if (F16) {
-                tmem_st16(colX + half * 32, reinterpret_cast<uint32_t(&)[16]>(v0));
-                tmem_st16(colX + half * 32 + 16, reinterpret_cast<uint32_t(&)[16]>(v1));
-              } else {
-                tmem_st32(colY + col0, v0);
-                tmem_st32(colY + col0 + 32, v1);
-              }
-              if (GRAD && active) *reinterpret_cast<uint2*>(maskws + (it * 128 + row) * 4 + half * 2) = make_uint2(bits0, bits1);
+              if (GRAD && active) *reinterpret_cast<uint2*>(maskws + (it * 128 + row) * 4 + half * 2) = make_uint2(bits[0], bits[1]);
             }
             tmem_wait_st();
             tc_fence_before();
@@ -797,28 +809,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
               ph_acc ^= 1;
               tc_fence_after();
               if (wact) {
-                uint32_t v0[32], v1[32];
-                tmem_ld32x2_sync(colY + col0, colY + col0 + 32, v0, v1);
-                if (F16) {
 #pragma unroll
-                  for (int j = 0; j < 32; j += 2) {
-                    const float a0 = ((bits.x >> j) & 1u) ? __uint_as_float(v0[j]) : 0.f;
-                    const float a1 = ((bits.x >> (j + 1)) & 1u) ? __uint_as_float(v0[j + 1]) : 0.f;
-                    const float c0 = ((bits.y >> j) & 1u) ? __uint_as_float(v1[j]) : 0.f;
-                    const float c1 = ((bits.y >> (j + 1)) & 1u) ? __uint_as_float(v1[j + 1]) : 0.f;
-                    v0[j >> 1] = pack_h2(a0, a1);   // j/2 <= j: slots already consumed
-                    v1[j >> 1] = pack_h2(c0, c1);
-                  }
-                  tmem_st16(colX + half * 32, reinterpret_cast<uint32_t(&)[16]>(v0));
-                  tmem_st16(colX + half * 32 + 16, reinterpret_cast<uint32_t(&)[16]>(v1));
-                } else {
+                for (int hh = 0; hh < 2; ++hh) {
+                  uint32_t v[32];
+                  tmem_ld32_sync(colY + col0 + 32 * hh, v);
+                  const uint32_t mb = hh ? bits.y : bits.x;
+                  if (F16) {
 #pragma unroll
-                  for (int j = 0; j < 32; ++j) {
-                    v0[j] = ((bits.x >> j) & 1u) ? tf32_round_bits(v0[j]) : 0u;
-                    v1[j] = ((bits.y >> j) & 1u) ? tf32_round_bits(v1[j]) : 0u;
+                    for (int j = 0; j < 32; j += 2) {
+                      const float a0 = ((mb >> j) & 1u) ? __uint_as_float(v[j]) : 0.f;
+                      const float a1 = ((mb >> (j + 1)) & 1u) ? __uint_as_float(v[j + 1]) : 0.f;
+                      v[j >> 1] = pack_h2(a0, a1);   // j/2 <= j: slot already consumed
+                    }
+                    tmem_st16(colX + half * 32 + 16 * hh, reinterpret_cast<uint32_t(&)[16]>(v));
+                  } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = ((mb >> j) & 1u) ? tf32_round_bits(v[j]) : 0u;
+                    tmem_st32(colY + col0 + 32 * hh, v);
                   }
-                  tmem_st32(colY + col0, v0);
-                  tmem_st32(colY + col0 + 32, v1);
                 }
               }
               tmem_wait_st();
@@ -829,21 +837,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
               ph_acc ^= 1;
               tc_fence_after();
               if (wact) {
-                uint32_t v0[32], v1[32];
-                tmem_ld32x2_sync((F16 ? colY : colX) + col0, (F16 ? colY : colX) + col0 + 32, v0, v1);
                 float2 ax = make_float2(0.f, 0.f), ay = make_float2(0.f, 0.f);
 #pragma unroll
-                for (int j = 0; j < 64; j += 2) {
-                  const int c = col0 + j;
-                  const float2 wx = *reinterpret_cast<const float2*>(sw + OFF_W1X + c);
-                  const float2 wy = *reinterpret_cast<const float2*>(sw + OFF_W1Y + c);
-                  const float2 bb = *reinterpret_cast<const float2*>(sw + OFF_B1 + c);
-                  const float2 h = __ffma2_rn(wy, zy2, __ffma2_rn(wx, zx2, bb));
-                  const uint32_t r0 = j < 32 ? v0[j] : v1[j - 32];
-                  const uint32_t r1 = j < 32 ? v0[j + 1] : v1[j - 31];
-                  const float2 dh = make_float2(h.x > 0.f ? __uint_as_float(r0) : 0.f, h.y > 0.f ? __uint_as_float(r1) : 0.f);
-                  ax = __ffma2_rn(dh, wx, ax);
-                  ay = __ffma2_rn(dh, wy, ay);
+                for (int hh = 0; hh < 2; ++hh) {
+                  uint32_t v[32];
+                  tmem_ld32_sync((F16 ? colY : colX) + col0 + 32 * hh, v);
+#pragma unroll
+                  for (int j = 0; j < 32; j += 2) {
+                    const int c = col0 + 32 * hh + j;
+                    const float2 wx = *reinterpret_cast<const float2*>(sw + OFF_W1X + c);
+                    const float2 wy = *reinterpret_cast<const float2*>(sw + OFF_W1Y + c);
+                    const float2 bb = *reinterpret_cast<const float2*>(sw + OFF_B1 + c);
+                    const float2 h = __ffma2_rn(wy, zy2, __ffma2_rn(wx, zx2, bb));
+                    const float2 dh = make_float2(h.x > 0.f ? __uint_as_float(v[j]) : 0.f, h.y > 0.f ? __uint_as_float(v[j + 1]) : 0.f);
+                    ax = __ffma2_rn(dh, wx, ax);
+                    ay = __ffma2_rn(dh, wy, ay);
+                  }
                 }
                 // a point occurs at most once per item and the items of a chain run in order:
                 // plain read-modify-write, deterministic
