@@ -1,21 +1,17 @@
 // fp32 (CUDA-core FFMA) geodesic step kernel: the <=1e-4-per-step variant and the one
-// the single-decoder path (BASELINE config 2) needs, since 11-bit tensor-core operands destroy
-// the tiny adjacent-point differences there (SURVEY hard part 1).
+// the single-decoder path (BASELINE config 2) needs, since TF32 destroys the tiny
+// adjacent-point differences there (SURVEY hard part 1).
 //
-// Persistent CTAs (one per SM), each walking curves n = blockIdx.x, +gridDim.x, ... over `steps`
-// Adam steps.  Per step the curve is cut into windows of W points (W-1 segments; neighbouring
-// windows share one point).  ROW COMPACTION as in the tensor-core kernel: per decoder only the points
-// of the window that drew it (as left or right end of a segment) are gathered into the rows of
-// 128-row "items"; a (point, decoder) pair nobody drew is never evaluated (the reference evaluates
-// all K x T pairs and multiplies two thirds of them by zero).  Per window:
-//   draws -> per-decoder row lists -> forward items (register-tiled 128x128x128 / 128x64x128
-//   SGEMMs, activations staged transposed+swizzled in shared memory, weights streamed from L2 in
-//   16-row slabs) -> selected outputs accumulate into Diff[m][segment] = x_{d2}(t+1) - x_{d1}(t)
-//   -> energy (and poly-line length) -> backward items (input gradient only, layer-2 ReLU masks as
-//   bits in an L2-resident workspace, layer-1 mask recomputed) -> dz per point -> d(omega).
+// One CTA = one curve, persistent over `steps` Adam steps.  Per step the curve is cut into
+// tiles of 128 points (127 segments; neighbouring tiles share one point).  Per tile:
+//   forward of all K decoders (register-tiled 128x128x128 / 128x64x128 SGEMMs, activations
+//   staged transposed+swizzled in shared memory, weights streamed from L2 in 16-row slabs)
+//   -> selected outputs accumulate into Diff[m][segment] = x_{d2}(t+1) - x_{d1}(t)
+//   -> energy (and poly-line length) reduction
+//   -> backward of all K decoders (input gradient only, ReLU masks as bits / recomputed)
+//   -> dz -> d(omega) via the design-matrix row of each point.
 // Then the end-point penalty gradient and Adam, all in shared memory; omega/m/v touch HBM
-// once per launch.  Results do not depend on the order of the row lists (every point occurs at
-// most once per item; all reductions run in a fixed order): deterministic.
+// once per launch.  Everything is deterministic (fixed reduction trees, no atomics).
 #include "vlg_common.cuh"
 #include "vlg_kernels.h"
 
@@ -100,111 +96,69 @@ __device__ __forceinline__ float pre1(const float* sw, int c, float2 z) {
   return fmaf(sw[OFF_W1Y + c], z.y, fmaf(sw[OFF_W1X + c], z.x, sw[OFF_B1 + c]));
 }
 
-constexpr int SIMT_MAX_W = 512;   // points per window
-constexpr int SIMT_MAX_ITEMS = 288;  // >= K + 2*M*W/128 + 1 for K <= 254, M <= 4, W <= 512 ... checked on the host
-
 struct Smem {
   float* As;       // 128*128
   float* Bs;       // 2*16*128
+  float* Diff;     // M*128*52
+  uint8_t* mask2;  // K*128*16
+  uint8_t* sel;    // MAX_M*2*128
   float* sw;       // 576 small weights of the current decoder
+  float2* zs;      // 128
+  float2* dzs;     // 128
+  float* ts;       // 128
   float* coef;     // 64
   float* basis;    // 32*9
   float* om;       // 18 omega, 18 m, 18 v
   float* gacc;     // 18
   float* red;      // 8*20
-  int* cnt;        // 256
-  uint16_t* item;  // SIMT_MAX_ITEMS: decoder | tile << 8
-  float* Diff;     // M*W*52
-  float2* zs;      // W
-  float2* dzs;     // W
-  float* ts;       // W
-  uint8_t* sel;    // MAX_M*2*W
-  uint16_t* rows;  // K*W
 };
 
-constexpr int SFIX = 128 * 128 + 2 * BS_FLOATS + 576 + 64 + 4 * MAX_NPOLY * MAX_KB + (3 * 2 * MAX_KB + 2) +
-                     (2 * MAX_KB + 2) + 8 * 20 + 256 + SIMT_MAX_ITEMS / 2;
-
-__device__ __forceinline__ Smem carve(unsigned char* base, int M, int W) {
+__device__ __forceinline__ Smem carve(unsigned char* base, int M, int K) {
   Smem s;
   float* f = reinterpret_cast<float*>(base);
   s.As = f; f += 128 * 128;
   s.Bs = f; f += 2 * BS_FLOATS;
+  s.Diff = f; f += M * 128 * DIFF_STRIDE;
   s.sw = f; f += 576;
+  s.zs = reinterpret_cast<float2*>(f); f += 256;
+  s.dzs = reinterpret_cast<float2*>(f); f += 256;
+  s.ts = f; f += 128;
   s.coef = f; f += 64;
   s.basis = f; f += 4 * MAX_NPOLY * MAX_KB;
   s.om = f; f += 3 * 2 * MAX_KB + 2;
   s.gacc = f; f += 2 * MAX_KB + 2;
   s.red = f; f += 8 * 20;
-  s.cnt = reinterpret_cast<int*>(f); f += 256;
-  s.item = reinterpret_cast<uint16_t*>(f); f += SIMT_MAX_ITEMS / 2;
-  s.Diff = f; f += M * W * DIFF_STRIDE;
-  s.zs = reinterpret_cast<float2*>(f); f += 2 * W;
-  s.dzs = reinterpret_cast<float2*>(f); f += 2 * W;
-  s.ts = f; f += W;
-  s.sel = reinterpret_cast<uint8_t*>(f); f += MAX_M * 2 * W / 4 + 1;
-  s.rows = reinterpret_cast<uint16_t*>(f);
+  s.sel = reinterpret_cast<uint8_t*>(f); f += MAX_M * 2 * 128 / 4;
+  s.mask2 = reinterpret_cast<uint8_t*>(f);  // replaced by a workspace slice when K is too large for shared memory
+  (void)K;
   return s;
 }
 
 }  // namespace
 
-static size_t simt_smem_bytes_w(int W, int K, int M) {
-  size_t fl = size_t(SFIX) + size_t(M) * W * DIFF_STRIDE + 2 * size_t(W) + 2 * size_t(W) + W + MAX_M * 2 * size_t(W) / 4 + 1;
-  return fl * 4 + size_t(K) * W * 2 + 16;
+static size_t simt_smem_base_bytes(int M) {
+  size_t fl = 128 * 128 + 2 * BS_FLOATS + size_t(M) * 128 * DIFF_STRIDE + 576 + 256 + 256 + 128 + 64 +
+              4 * MAX_NPOLY * MAX_KB + (3 * 2 * MAX_KB + 2) + (2 * MAX_KB + 2) + 8 * 20 + MAX_M * 2 * 128 / 4;
+  return fl * 4;
 }
-static int simt_max_items(int W, int K, int M) { return K + 2 * M * W / 128 + 1; }
-
-// Window length: fewest 128-row items per curve under the shared-memory budget (same expected-cost
-// model as the tensor-core kernel: a decoder is drawn by a point with probability 1-(1-1/K)^(2M)).
-static int simt_window_points(int T, int K, int M) {
-  const double p = 1.0 - pow(1.0 - 1.0 / K, 2.0 * M);
-  const int segs = T - 1;
-  int best_w = 0;
-  double best = 1e300;
-  for (int nwin = 1; nwin <= segs; ++nwin) {
-    const int w = (segs + nwin - 1) / nwin + 1;
-    if (w <= SIMT_MAX_W && simt_smem_bytes_w(w, K, M) <= 232448 && simt_max_items(w, K, M) <= SIMT_MAX_ITEMS) {
-      const double mean = w * p, sd = sqrt(w * p * (1.0 - p)) + 1e-9;
-      double items = 0.0;
-      for (int q = 0; q * 128 < w; ++q) items += 0.5 * erfc((q * 128 + 0.5 - mean) / (sd * 1.4142135623730951));
-      const double cost = nwin * (K * items + 0.25);
-      if (cost < best) { best = cost; best_w = w; }
-    }
-    if (w <= 128) break;
-  }
-  return best_w;  // 0: does not fit
+static bool simt_masks_in_smem(int M, int K) { return simt_smem_base_bytes(M) + size_t(K) * 2048 <= 232448; }
+static int simt_grid(int N, int M, int K) {
+  if (simt_masks_in_smem(M, K)) return N;   // one CTA per curve, scheduled by the hardware
+  return N < 296 ? N : 296;                 // persistent CTAs, each with a mask slice in the workspace
 }
-static int simt_grid(int N) {
-  int dev = 0, sms = 148;
-  if (cudaGetDevice(&dev) == cudaSuccess) {
-    int v = 0;
-    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) sms = v;
-  } else {
-    (void)cudaGetLastError();
-  }
-  return N < sms ? N : sms;
-}
-size_t simt_smem_bytes(int T, int K, int M) {
-  const int W = simt_window_points(T, K, M);
-  return W ? simt_smem_bytes_w(W, K, M) : size_t(1) << 30;
-}
-// layer-2 ReLU mask bits [cta][item][128 rows][16 bytes], L2 resident
-size_t simt_workspace_bytes(int N, int T, int K, int M) {
-  const int W = simt_window_points(T, K, M);
-  if (W == 0) return 0;
-  return size_t(simt_grid(N)) * simt_max_items(W, K, M) * 2048;
+size_t simt_smem_bytes(int M, int K) { return simt_smem_base_bytes(M) + (simt_masks_in_smem(M, K) ? size_t(K) * 2048 : 0); }
+// layer-2 ReLU mask bits [cta][K][128 rows][16 bytes] when they do not fit in shared memory
+size_t simt_workspace_bytes(int N, int K, int M) {
+  return simt_masks_in_smem(M, K) ? 0 : size_t(simt_grid(N, M, K)) * K * 2048;
 }
 
 template <bool GRAD>
-__global__ void __launch_bounds__(NTHREADS, 1) simt_curve_kernel(StepParams p, int W, int max_items) {
+__global__ void __launch_bounds__(NTHREADS, 1) simt_curve_kernel(StepParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, lane = tid & 31, warp = tid >> 5;
   const int M = p.M, K = p.K, T = p.T, n_poly = p.n_poly, Kb = p.Kb, X = p.X;
-  Smem s = carve(smem_raw, M, W);
-  uint8_t* mask2 = reinterpret_cast<uint8_t*>(p.workspace) + size_t(blockIdx.x) * max_items * 2048;
-  const int WSEG = W - 1;
-  const int nwin = (T - 1 + WSEG - 1) / WSEG;
+  Smem s = carve(smem_raw, M, K);
+  if (p.workspace != nullptr) s.mask2 = reinterpret_cast<uint8_t*>(p.workspace) + size_t(blockIdx.x) * K * 2048;
   for (int i = tid; i < 4 * n_poly * Kb; i += NTHREADS) s.basis[i] = p.basis[i];
 
   for (int n = blockIdx.x; n < p.N; n += gridDim.x) {
@@ -218,6 +172,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) simt_curve_kernel(StepParams p, i
   }
   const float2 pa = make_float2(p.a[2 * n], p.a[2 * n + 1]);
   const float2 pb = make_float2(p.b[2 * n], p.b[2 * n + 1]);
+  const int ntiles = (T - 1 + TILE_SEGS - 1) / TILE_SEGS;
   const float coefm = 2.0f / float(M);
   __syncthreads();
 
@@ -233,79 +188,49 @@ __global__ void __launch_bounds__(NTHREADS, 1) simt_curve_kernel(StepParams p, i
     float e_tot = 0.f, l_tot = 0.f;  // meaningful in thread 0
     __syncthreads();
 
-    for (int win = 0; win < nwin; ++win) {
-      const int seg0 = win * WSEG;
-      const int nseg = min(WSEG, T - 1 - seg0);
-      // ---- window setup: points, draws, clear accumulators ----
-      for (int pt = tid; pt < W; pt += NTHREADS) {
-        const int ti = min(seg0 + pt, T - 1);
+    for (int tile = 0; tile < ntiles; ++tile) {
+      const int seg0 = tile * TILE_SEGS;
+      const int nseg = min(TILE_SEGS, T - 1 - seg0);
+      // ---- tile setup: points, draws, clear accumulators ----
+      if (tid < TILE_ROWS) {
+        const int ti = min(seg0 + tid, T - 1);
         const float t = p.t[ti];
-        s.ts[pt] = t;
-        s.zs[pt] = spline_point(t, n_poly, s.coef, pa, pb);
-        s.dzs[pt] = make_float2(0.f, 0.f);
+        s.ts[tid] = t;
+        s.zs[tid] = spline_point(t, n_poly, s.coef, pa, pb);
+        s.dzs[tid] = make_float2(0.f, 0.f);
         if (p.draws != nullptr) {
           for (int m = 0; m < M; ++m)
             for (int role = 0; role < 2; ++role) {
               uint8_t v = 255;
-              if (pt < nseg)
-                v = p.draws[(((size_t(n) * p.steps + step) * M + m) * 2 + role) * size_t(T - 1) + seg0 + pt];
-              s.sel[(m * 2 + role) * W + pt] = v;
+              if (tid < nseg)
+                v = p.draws[(((size_t(n) * p.steps + step) * M + m) * 2 + role) * size_t(T - 1) + seg0 + tid];
+              s.sel[(m * 2 + role) * 128 + tid] = v;
             }
         } else {
           for (int jp = 0; jp < (M + 1) / 2; ++jp) {
             uint32_t d[4] = {255u, 255u, 255u, 255u};
-            if (pt < nseg)
-              counter_draws4(p.seed, uint32_t(p.curve_id0 + n), uint32_t(p.step0 + step), uint32_t(seg0 + pt),
+            if (tid < nseg)
+              counter_draws4(p.seed, uint32_t(p.curve_id0 + n), uint32_t(p.step0 + step), uint32_t(seg0 + tid),
                              uint32_t(jp), uint32_t(K), d);
             for (int q = 0; q < 4; ++q) {
               const int m = 2 * jp + (q >> 1);
-              if (m < M) s.sel[(m * 2 + (q & 1)) * W + pt] = uint8_t(d[q]);
+              if (m < M) s.sel[(m * 2 + (q & 1)) * 128 + tid] = uint8_t(d[q]);
             }
           }
         }
       }
-      for (int i = tid; i < M * W * DIFF_STRIDE / 4; i += NTHREADS)
+      for (int i = tid; i < M * 128 * DIFF_STRIDE / 4; i += NTHREADS)
         reinterpret_cast<float4*>(s.Diff)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int i = tid; i < K; i += NTHREADS) s.cnt[i] = 0;
       __syncthreads();
-      // ---- per-decoder row lists: the points of the window that drew decoder k ----
-      for (int pt = tid; pt <= nseg; pt += NTHREADS) {
-        int cand[2 * MAX_M];
-        int nc = 0;
-        for (int m = 0; m < M; ++m) {
-          if (pt < nseg) cand[nc++] = s.sel[(m * 2 + 0) * W + pt];
-          if (pt >= 1) cand[nc++] = s.sel[(m * 2 + 1) * W + pt - 1];
-        }
-        for (int i = 0; i < nc; ++i) {
-          bool dup = false;
-          for (int j = 0; j < i; ++j) dup |= (cand[j] == cand[i]);
-          if (!dup) {
-            const int slot = atomicAdd(&s.cnt[cand[i]], 1);
-            s.rows[cand[i] * W + slot] = uint16_t(pt);
-          }
-        }
-      }
-      __syncthreads();
-      if (tid == 0) {
-        int ni = 0;
-        for (int k = 0; k < K; ++k)
-          for (int q = 0; q * 128 < s.cnt[k]; ++q) s.item[ni++] = uint16_t(k | (q << 8));
-        s.red[159] = __int_as_float(ni);
-      }
-      __syncthreads();
-      const int nitems = __float_as_int(s.red[159]);
 
       // =============================== forward ===============================
-      for (int it = 0; it < nitems; ++it) {
-        const int k = s.item[it] & 0xFF, q0 = (s.item[it] >> 8) * 128;
-        const int nrows = min(128, s.cnt[k] - q0);
-        const uint16_t* rl = s.rows + k * W + q0;
+      for (int k = 0; k < K; ++k) {
         const float* dec = dec_ptr(p.packed, k);
         for (int i = tid; i < 576; i += NTHREADS) s.sw[i] = __ldg(dec + i);
         __syncthreads();
         {  // layer 1 on CUDA cores -> As[c][row]
           const int row = tid & 127, c0 = (tid >> 7) * 64;
-          const float2 z = s.zs[row < nrows ? rl[row] : 0];
+          const float2 z = s.zs[row];
 #pragma unroll 8
           for (int c = c0; c < c0 + 64; ++c) s.As[as_idx(c, row)] = fmaxf(pre1(s.sw, c, z), 0.f);
         }
@@ -326,7 +251,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) simt_curve_kernel(StepParams p, i
               if (v > 0.f) bits |= 1u << j;
               acc[i][j] = fmaxf(v, 0.f);
             }
-            if (GRAD) mask2[(size_t(it) * 128 + 8 * ty + i) * 16 + tx] = uint8_t(bits);
+            if (GRAD) s.mask2[(size_t(k) * 128 + 8 * ty + i) * 16 + tx] = uint8_t(bits);
           }
           store_tile_T(s.As, acc);  // gemm_tile ended with a barrier: As is free
         }
@@ -339,20 +264,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) simt_curve_kernel(StepParams p, i
             for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
           gemm_tile<4>(s.As, s.Bs, dec + OFF_W3T, H, acc);
           const int c = 4 * tx;
-          int pts[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) pts[i] = (8 * ty + i < nrows) ? int(rl[8 * ty + i]) : -1;
           if (c < X) {
             float4 bb = *reinterpret_cast<const float4*>(s.sw + OFF_B3 + c);
-            // role 0: this point is the left end of its segment
+            // role 0: this row is the left point of its segment
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const int pt = pts[i];
+              const int r = 8 * ty + i;
               acc[i][0] += bb.x; acc[i][1] += bb.y; acc[i][2] += bb.z; acc[i][3] += bb.w;
-              if (pt < 0) continue;
               for (int m = 0; m < M; ++m)
-                if (s.sel[(m * 2 + 0) * W + pt] == k) {
-                  float4* d = reinterpret_cast<float4*>(s.Diff + (m * W + pt) * DIFF_STRIDE + c);
+                if (s.sel[(m * 2 + 0) * 128 + r] == k) {
+                  float4* d = reinterpret_cast<float4*>(s.Diff + (m * 128 + r) * DIFF_STRIDE + c);
                   float4 v = *d;
                   v.x -= acc[i][0]; v.y -= acc[i][1]; v.z -= acc[i][2]; v.w -= acc[i][3];
                   *d = v;
@@ -361,14 +282,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) simt_curve_kernel(StepParams p, i
           }
           __syncthreads();
           if (c < X) {
-            // role 1: this point is the right end of the previous segment
+            // role 1: this row is the right point of the previous segment
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const int pt = pts[i];
-              if (pt < 1) continue;
+              const int r = 8 * ty + i;
+              if (r == 0) continue;
               for (int m = 0; m < M; ++m)
-                if (s.sel[(m * 2 + 1) * W + pt - 1] == k) {
-                  float4* d = reinterpret_cast<float4*>(s.Diff + (m * W + pt - 1) * DIFF_STRIDE + c);
+                if (s.sel[(m * 2 + 1) * 128 + r - 1] == k) {
+                  float4* d = reinterpret_cast<float4*>(s.Diff + (m * 128 + r - 1) * DIFF_STRIDE + c);
                   float4 v = *d;
                   v.x += acc[i][0]; v.y += acc[i][1]; v.z += acc[i][2]; v.w += acc[i][3];
                   *d = v;
@@ -382,14 +303,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) simt_curve_kernel(StepParams p, i
       // =============================== energy ===============================
       {
         float e = 0.f, l = 0.f;
-        for (int m = 0; m < M; ++m)
-          for (int r = tid; r < nseg; r += NTHREADS) {
-            const float* d = s.Diff + (m * W + r) * DIFF_STRIDE;
+        for (int idx = tid; idx < M * 128; idx += NTHREADS) {
+          const int r = idx & 127;
+          if (r < nseg) {
+            const float* d = s.Diff + idx * DIFF_STRIDE;
             float q = 0.f;
             for (int c = 0; c < X; ++c) q = fmaf(d[c], d[c], q);
             e += q;
             l += sqrtf(q);
           }
+        }
         e = warp_sum(e);
         l = warp_sum(l);
         if (lane == 0) { s.red[warp] = e; s.red[8 + warp] = l; }
@@ -405,27 +328,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) simt_curve_kernel(StepParams p, i
 
       if (GRAD) {
         // =============================== backward ===============================
-        for (int it = 0; it < nitems; ++it) {
-          const int k = s.item[it] & 0xFF, q0 = (s.item[it] >> 8) * 128;
-          const int nrows = min(128, s.cnt[k] - q0);
-          const uint16_t* rl = s.rows + k * W + q0;
+        for (int k = 0; k < K; ++k) {
           const float* dec = dec_ptr(p.packed, k);
           for (int i = tid; i < 576; i += NTHREADS) s.sw[i] = __ldg(dec + i);
           {  // G = dE/dx_k  -> As[c][row], c < 64
             const int row = tid & 127, c0 = (tid >> 7) * 32;
-            const int pt = row < nrows ? int(rl[row]) : -1;
             float g[32];
 #pragma unroll
             for (int c = 0; c < 32; ++c) g[c] = 0.f;
-            for (int m = 0; m < (pt >= 0 ? M : 0); ++m) {
-              if (pt >= 1 && s.sel[(m * 2 + 1) * W + pt - 1] == k) {
-                const float* d = s.Diff + (m * W + pt - 1) * DIFF_STRIDE;
+            for (int m = 0; m < M; ++m) {
+              if (row >= 1 && s.sel[(m * 2 + 1) * 128 + row - 1] == k) {
+                const float* d = s.Diff + (m * 128 + row - 1) * DIFF_STRIDE;
 #pragma unroll
                 for (int c = 0; c < 32; ++c)
                   if (c0 + c < X) g[c] += d[c0 + c];
               }
-              if (s.sel[(m * 2 + 0) * W + pt] == k) {
-                const float* d = s.Diff + (m * W + pt) * DIFF_STRIDE;
+              if (s.sel[(m * 2 + 0) * 128 + row] == k) {
+                const float* d = s.Diff + (m * 128 + row) * DIFF_STRIDE;
 #pragma unroll
                 for (int c = 0; c < 32; ++c)
                   if (c0 + c < X) g[c] -= d[c0 + c];
@@ -443,7 +362,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) simt_curve_kernel(StepParams p, i
           gemm_tile<8>(s.As, s.Bs, dec + OFF_W3, XP, acc);  // dh2 = G W3
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const uint32_t bits = mask2[(size_t(it) * 128 + 8 * ty + i) * 16 + tx];
+            const uint32_t bits = s.mask2[(size_t(k) * 128 + 8 * ty + i) * 16 + tx];
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               if (!((bits >> j) & 1u)) acc[i][j] = 0.f;
@@ -459,8 +378,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) simt_curve_kernel(StepParams p, i
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int r = 8 * ty + i;
-            const int pt = r < nrows ? int(rl[r]) : -1;     // uniform over the 16 column threads of the row
-            const float2 z = s.zs[pt < 0 ? 0 : pt];
+            const float2 z = s.zs[r];
             float dx = 0.f, dy = 0.f;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -475,44 +393,37 @@ __global__ void __launch_bounds__(NTHREADS, 1) simt_curve_kernel(StepParams p, i
               dx += __shfl_xor_sync(0xffffffffu, dx, o);
               dy += __shfl_xor_sync(0xffffffffu, dy, o);
             }
-            // a point occurs at most once per item and items run one after the other: plain read-modify-write
-            if (tx == 0 && pt >= 0) {
-              float2 d = s.dzs[pt];
+            if (tx == 0) {
+              float2 d = s.dzs[r];
               d.x += dx;
               d.y += dy;
-              s.dzs[pt] = d;
+              s.dzs[r] = d;
             }
           }
           __syncthreads();
         }
-        // ---- d(omega) += P^T dz over the points of the window ----
-        for (int base = 0; base < W; base += NTHREADS) {
-          const int pt = base + tid;
+        // ---- d(omega) += P^T dz for this tile ----
+        {
           float P[MAX_KB];
           float2 dz = make_float2(0.f, 0.f);
-          if (pt < W) {
-            design_row(s.ts[pt], n_poly, Kb, s.basis, P);
-            dz = s.dzs[pt];
-          } else {
-#pragma unroll
-            for (int k = 0; k < MAX_KB; ++k) P[k] = 0.f;
+          if (tid < TILE_ROWS) {
+            design_row(s.ts[tid], n_poly, Kb, s.basis, P);
+            dz = s.dzs[tid];
           }
+          if (warp < 4) {
 #pragma unroll
-          for (int k = 0; k < MAX_KB; ++k)
-            if (k < Kb) {
-              float cx = warp_sum(P[k] * dz.x), cy = warp_sum(P[k] * dz.y);
-              if (lane == 0) { s.red[warp * 20 + 2 * k] = cx; s.red[warp * 20 + 2 * k + 1] = cy; }
-            }
+            for (int k = 0; k < MAX_KB; ++k)
+              if (k < Kb) {
+                float cx = warp_sum(P[k] * dz.x), cy = warp_sum(P[k] * dz.y);
+                if (lane == 0) { s.red[warp * 20 + 2 * k] = cx; s.red[warp * 20 + 2 * k + 1] = cy; }
+              }
+          }
           __syncthreads();
-          if (tid < 2 * Kb) {
-            float g = 0.f;
-            for (int w = 0; w < 8; ++w) g += s.red[w * 20 + tid];
-            s.gacc[tid] += g;
-          }
+          if (tid < 2 * Kb) s.gacc[tid] += (s.red[tid] + s.red[20 + tid]) + (s.red[40 + tid] + s.red[60 + tid]);
           __syncthreads();
         }
       }
-    }  // windows
+    }  // tiles
 
     // ---- step epilogue: energy out, penalty gradient, Adam ----
     if (tid == 0) {
@@ -551,21 +462,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) simt_curve_kernel(StepParams p, i
 }
 
 cudaError_t launch_simt(const StepParams& p, bool grad, cudaStream_t stream) {
-  const int W = simt_window_points(p.T, p.K, p.M);
-  if (W < 2) return cudaErrorNotSupported;
-  const size_t smem = simt_smem_bytes_w(W, p.K, p.M);
-  const int grid = simt_grid(p.N);
-  const int max_items = simt_max_items(W, p.K, p.M);
-  if (p.workspace == nullptr || p.workspace_bytes < simt_workspace_bytes(p.N, p.T, p.K, p.M)) return cudaErrorInvalidValue;
+  const size_t smem = simt_smem_bytes(p.M, p.K);
+  const int grid = simt_grid(p.N, p.M, p.K);
+  StepParams q = p;
+  if (simt_masks_in_smem(p.M, p.K)) {
+    q.workspace = nullptr;
+  } else if (p.workspace == nullptr || p.workspace_bytes < simt_workspace_bytes(p.N, p.K, p.M)) {
+    return cudaErrorInvalidValue;
+  }
   cudaError_t e;
   if (grad) {
     e = cudaFuncSetAttribute(simt_curve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
-    simt_curve_kernel<true><<<grid, NTHREADS, smem, stream>>>(p, W, max_items);
+    simt_curve_kernel<true><<<grid, NTHREADS, smem, stream>>>(q);
   } else {
     e = cudaFuncSetAttribute(simt_curve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
-    simt_curve_kernel<false><<<grid, NTHREADS, smem, stream>>>(p, W, max_items);
+    simt_curve_kernel<false><<<grid, NTHREADS, smem, stream>>>(q);
   }
   return cudaGetLastError();
 }

@@ -44,7 +44,10 @@ def test_sizes_and_argument_errors_without_gpu(built_lib):
     assert n > 10 * (2 * 128 + 128 + 128 * 128 + 128 + 50 * 128 + 50) * 4
     assert lib.vlg_packed_decoders_bytes(10, 64, 50) == 0      # H must be 128
     assert lib.vlg_packed_decoders_bytes(10, 128, 100) == 0    # X too wide
-    assert lib.vlg_workspace_bytes(45, 2000, 4, 10, 2, 0) == 0
+    # fp32 kernel: ReLU-mask scratch per persistent CTA (<= one CTA per curve): whole 2 KB items
+    ws = lib.vlg_workspace_bytes(45, 2000, 4, 10, 2, 0)
+    assert ws > 0 and ws % (45 * 2048) == 0
+    assert lib.vlg_workspace_bytes(45, 2000, 4, 10, 2, 3) == lib.vlg_workspace_bytes(45, 2000, 4, 10, 2, 1) > 0
     # null pointers are rejected before any CUDA call
     rc = lib.vlg_optimize_steps(None, 10, 4, 2000, 4, 2, 1, 0, None, None, None, None, None, None, None, None,
                                 0, 0, 1e-3, 0.9, 0.999, 1e-8, 1000.0, None, None, 0, None, 0, None)

@@ -108,8 +108,9 @@ int fill_params(vlg::StepParams* p, const void* packed, int K_active, int N, int
 int dispatch(const vlg::StepParams& p, bool grad, cudaStream_t stream) {
   cudaError_t e;
   if (p.precision == VLG_PRECISION_FP32) {
-    if (vlg::simt_smem_bytes(p.M, p.K) > 232448) return VLG_ERR_UNSUPPORTED;
+    if (vlg::simt_smem_bytes(p.T, p.K, p.M) > 232448) return VLG_ERR_UNSUPPORTED;
     e = vlg::launch_simt(p, grad, stream);
+    if (e == cudaErrorNotSupported) return VLG_ERR_UNSUPPORTED;
   } else {
     e = vlg::launch_tc(p, grad, stream);
     if (e == cudaErrorNotSupported) return VLG_ERR_UNSUPPORTED;
@@ -157,7 +158,7 @@ int vlg_pack_decoders(const float* W1, const float* b1, const float* W2, const f
 
 size_t vlg_workspace_bytes(int N, int T, int n_poly, int K_active, int M, int precision) {
   (void)n_poly;
-  if (precision == VLG_PRECISION_FP32) return vlg::simt_workspace_bytes(N, K_active, M);
+  if (precision == VLG_PRECISION_FP32) return vlg::simt_workspace_bytes(N, T, K_active, M);
   return vlg::tc_workspace_bytes(N, T, K_active, M);
 }
 

@@ -32,8 +32,8 @@ struct StepParams {
   int precision;
 };
 
-size_t simt_smem_bytes(int M, int K);
-size_t simt_workspace_bytes(int N, int K, int M);
+size_t simt_smem_bytes(int T, int K, int M);
+size_t simt_workspace_bytes(int N, int T, int K, int M);
 cudaError_t launch_simt(const StepParams& p, bool grad, cudaStream_t stream);
 
 size_t tc_workspace_bytes(int N, int T, int K, int M);

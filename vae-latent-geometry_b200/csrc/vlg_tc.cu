@@ -1029,7 +1029,11 @@ cudaError_t launch_tc(const StepParams& p, bool grad, cudaStream_t stream) {
   const size_t smem = tc_smem_fixed_bytes(W, p.K, p.M) + size_t(2) * nst * STAGE_BYTES;
   const int grid = tc_grid(p.N);
   StepParams q = p;
-  const int nchunks = q.steps < 4 ? q.steps : 4;          // chunks of a curve per launch
+  // chunks of a curve per launch: at least 4, and enough work units (~48 per CTA) that the last wave's
+  // tail -- at most one unit -- stays a small fraction of the launch
+  int nchunks = (48 * grid + p.N - 1) / p.N;
+  if (nchunks < 4) nchunks = 4;
+  if (nchunks > q.steps) nchunks = q.steps;
   q.unit_steps = (q.steps + nchunks - 1) / nchunks;
   cudaError_t e = cudaMemsetAsync(p.workspace, 0, tc_queue_words(p.N) * 4, stream);
   if (e != cudaSuccess) return e;
