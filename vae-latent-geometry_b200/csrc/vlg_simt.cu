@@ -69,10 +69,17 @@ __device__ __forceinline__ void gemm_tile(const float* __restrict__ As, float* _
         float4 b1 = *reinterpret_cast<const float4*>(B + kk * N + 64 + 4 * tx);
         bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
       }
+      // packed f32x2 FMAs (two independent IEEE fmas per instruction: same bits as scalar fmaf, half the issue slots)
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < 8; ++i) {
+        const float2 a2 = make_float2(av[i], av[i]);
 #pragma unroll
-        for (int j = 0; j < NT; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        for (int j = 0; j < NT; j += 2) {
+          const float2 r = __ffma2_rn(a2, make_float2(bv[j], bv[j + 1]), make_float2(acc[i][j], acc[i][j + 1]));
+          acc[i][j] = r.x;
+          acc[i][j + 1] = r.y;
+        }
+      }
     }
     if (c + 1 < nchunks) {
       float4* dst = reinterpret_cast<float4*>(Bs + ((c + 1) & 1) * BS_FLOATS);
