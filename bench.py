@@ -229,13 +229,15 @@ def run_gpu_arm(args):
     def launch(nsteps):
         return vlg_b200.optimize_splines(model, dec, t, nsteps, M=M_MC, seed=0, curve_id0=lo, precision=args.precision)
 
+    # clocks are sampled (nvidia-smi, 100 ms period) from the warm-up on: the timed region of a sharded run can
+    # be shorter than one sampling period, so the same load is kept up before and after it (see below)
+    sampler = ClockSampler(dev.index)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         launch(1)
     barrier()
 
     # ---- value: K steps, state resident in HBM ----
-    sampler = ClockSampler(dev.index)
-    sampler.start()
     kernel_ms, launches = 0.0, 0
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -255,7 +257,13 @@ def run_gpu_arm(args):
         done += ns
     ev1.record()
     barrier()
+    # untimed tail under the same load until the sampler has seen the GPU busy at least three times
+    t_tail = time.time()
+    while len(sampler.rows) < 3 and time.time() - t_tail < 2.0:
+        launch(1)
+        torch.cuda.synchronize()
     clocks = sampler.stop()
+    clocks["window"] = "warm-up + timed region + same-load tail"
     ms_total = ev0.elapsed_time(ev1)
     kernel_ms = sum(x.elapsed_time(y) for x, y, _ in kernel_events)
 
