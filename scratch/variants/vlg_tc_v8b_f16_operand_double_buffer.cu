@@ -1,0 +1,1321 @@
+// tcgen05 (TF32) geodesic step kernel -- the tensor-core variant (<=1e-3 relative on lengths).
+//
+// Persistent CTAs (one per SM, 608 threads) pull work units -- (curve, chunk of Adam steps) -- from
+// a global queue; a curve's chunks are chained through its omega/m/v in HBM, so a launch of
+// `steps` steps has no tail longer than one chunk.  The two 128-wide decoder layers and their
+// transposes run as tcgen05.mma kind::tf32 with
+//   * M = 128 rows = the 128 TMEM lanes,
+//   * the A operand (activations) living in TENSOR MEMORY: the epilogue threads write the
+//     next layer's input back with tcgen05.st, in place of the accumulator they just read,
+//   * the B operand (weights) streamed from L2 into per-chain shared-memory rings by the TMA
+//     engine (1-D bulk copies of pre-packed no-swizzle K-major images, mbarrier complete_tx),
+//   * fp32 accumulators in TMEM, read back with tcgen05.ld.
+//
+// ROW COMPACTION.  The MC energy touches, per curve point, only the decoders drawn for the two
+// segments that meet there (<= 2M of K; 3.4 of 10 on average), and the reference's dense
+// K x T forward/backward spends two thirds of its FLOPs on outputs that are multiplied by zero.
+// Here a curve is cut into windows of W points (W chosen on the host so that a decoder is drawn by
+// ~115 points of a window on average; W-1 segments); for every decoder the points
+// of the window that drew it are gathered into the rows of one 128-row MMA tile ("item"; a
+// decoder drawn by more than 128 points simply gets several items).  Results are identical:
+// each selected (point, decoder) pair goes through exactly the same arithmetic.
+//
+// Warp roles: warps 0/1 = weight producers of chain 0/1 (one lane each), warp 2 = MMA issuer
+// (one lane), warps 3-10 and 11-18 = two epilogue groups of 8 warps.  Each group owns a "chain"
+// of 256 TMEM columns and every other item.  The MMA issuer serves whichever chain has its
+// operand ready, which is why every chain has its own weight ring.  Inside a group two threads
+// share a row (TMEM lane) and split its columns: four epilogue warps per scheduler hide TMEM /
+// shared-memory latency.
+//
+// Per window: draws -> per-decoder row lists (shared-memory atomics; row order does not affect
+// any result) -> forward items (layer 1 on CUDA cores, exact fp32) -> selected outputs stored
+// with plain stores, one writer per slot (left-end output x1 of a segment in shared memory,
+// right-end output x2 in an L2-resident workspace) -> one pass forms x2-x1 and the energy ->
+// backward items (input gradient only; layer-2 ReLU masks as bits in the workspace, layer-1
+// mask recomputed) -> dz per point -> d(omega).  Penalty gradient and Adam as in vlg_simt.cu.
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
+#include "vlg_common.cuh"
+#include "vlg_kernels.h"
+#include "vlg_tcgen05.cuh"
+
+namespace vlg {
+
+#ifdef VLG_TC_STATS
+// debug build only: per-CTA wait-cycle counters [cta][8]
+__device__ long long g_tc_stats[1024 * 8];
+#define STAT_T0() long long _t0 = clock64()
+#define STAT_ADD(var) var += clock64() - _t0
+#else
+#define STAT_T0()
+#define STAT_ADD(var)
+#endif
+
+namespace {
+
+using namespace tc;
+
+constexpr int TC_THREADS = 608;       // 3 control warps + 16 epilogue warps
+constexpr int GROUP_THREADS = 256;    // one epilogue group (chain)
+constexpr int EPI_THREADS = 512;
+constexpr int FIRST_EPI_WARP = 3;
+constexpr int STAGE_BYTES = 16384;
+constexpr int MAX_STAGES = 4;         // per chain
+constexpr int XD_STRIDE = 52;         // floats per stored decoder output row (X <= 52; 16 B rows)
+constexpr int TC_MAX_W = 512;         // curve points per window (runtime W <= this); neighbouring windows share one point
+constexpr int TC_MAX_M = 2;           // MC samples supported by this kernel
+constexpr int TC_MAX_K = 64;          // decoders
+constexpr int MAX_ITEMS = TC_MAX_K + 16;  // sum_k ceil(n_k/128) <= K + 2*M*W/128
+
+// the four tensor-core GEMMs of one decoder
+struct OpInfo {
+  int img_off;   // float offset of the B image inside the decoder record
+  int nstages;   // 16 KB stages
+  int n;         // MMA N
+  int nk;        // MMAs per stage (8 TMEM columns of A each: 8 tf32 or 16 fp16 contraction indices)
+  int a_col;     // chain-relative TMEM column of A
+  int d_col;     // chain-relative TMEM column of D
+};
+// kind::tf32: activations are fp32 words with TF32-rounded bits, one per TMEM column; an accumulator is
+// overwritten in place by the next layer's operand (X = columns 0..127 of the chain, Y = 128..255).
+// kind::f16 : activations are fp16 pairs, two per column, so an operand takes half the columns of the
+// accumulator it was computed from and cannot be written in place (another thread's accumulator
+// columns would be hit).  All accumulators go to Y; X holds TWO operand buffers of 64 columns that
+// alternate from item to item, so that the next item's first operand (layer-1 output, or dE/dx) is
+// written while the current item's last MMA still reads the other buffer.
+template <bool F16>
+__device__ __forceinline__ OpInfo op_info(int op) {
+  if (F16) {
+    switch (op) {
+      // operand buffer b = (item index of the chain) & 1 at X[64 b : 64 b + 64] (added by the issuer)
+      case 0: return {OFF_W2_H, 2, 128, 4, 0, 128};     // F2: D2(Y) = A1(Xb) * W2^T
+      case 1: return {OFF_W3_H, 1, 64, 8, 0, 128};      // F3: D3(Y[0:64]) = A2(Xb) * W3^T
+      case 2: return {OFF_W3T_H, 1, 128, 4, 0, 128};    // B3: D4(Y) = G(Xb[0:32]) * W3
+      default: return {OFF_W2T_H, 2, 128, 4, 0, 128};   // B2: D5(Y) = A4(Xb) * W2
+    }
+  }
+  switch (op) {
+    case 0: return {OFF_W2_UMMA, 4, 128, 4, 0, 128};    // F2: D2(Y) = A1(X) * W2^T
+    case 1: return {OFF_W3_UMMA, 2, 64, 8, 128, 0};     // F3: D3(X[0:64]) = A2(Y) * W3^T
+    case 2: return {OFF_W3T_UMMA, 2, 128, 4, 0, 128};   // B3: D4(Y) = G(X[0:64]) * W3
+    default: return {OFF_W2T_UMMA, 4, 128, 4, 128, 0};  // B2: D5(X) = A4(Y) * W2
+  }
+}
+// two fp32 -> one fp16x2 word (round-to-nearest; lo half = first argument), optionally through relu
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t pack_relu_h2(float a, float b) {
+  const __half2 h = __hmax2(__floats2half2_rn(a, b), __float2half2_rn(0.f));
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+// Backward quantities (dE/dx and the hidden-layer gradients) are scaled by 2^6 before they are rounded to
+// fp16 and unscaled in fp32 when dz is accumulated: gradients of a converged curve are O(1e-2 .. 1e-5)
+// per element, fp16 loses precision below 6e-5.
+constexpr float F16_GRAD_SCALE = 64.f;
+
+// round-to-nearest to TF32 for finite values: the tensor core ignores the 13 low mantissa bits
+__device__ __forceinline__ uint32_t tf32_round_bits(uint32_t b) { return b + 0x1000u; }
+// relu, then TF32 round-to-nearest on the bit pattern.  (An integer-max formulation,
+// max(int(bits + 0x1000), 0), produced wrong results when combined with the packed f32x2
+// intrinsics under nvcc 12.9 -- keep the float max.)
+__device__ __forceinline__ uint32_t relu_tf32(float v) { return __float_as_uint(fmaxf(v, 0.f)) + 0x1000u; }
+
+__device__ __forceinline__ void named_bar(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
+// work-queue header at the start of the workspace: 64 words + one progress word per curve, 256 B aligned
+__host__ __device__ inline size_t tc_queue_words(int N) { return (size_t(64 + N) + 63) / 64 * 64; }
+
+struct WinCtl {
+  int nitems;
+  int pad;
+  uint16_t item[MAX_ITEMS];  // decoder | pass << 8
+};
+
+// Wait for the chain's accumulator.  VLG_TC_WAIT_MODE 0: every lane polls the mbarrier; 1: lane 0
+// polls and the warp reconverges on __syncwarp (32x fewer mbarrier probes in the memory queue).
+#ifndef VLG_TC_WAIT_MODE
+#define VLG_TC_WAIT_MODE 0
+#endif
+__device__ __forceinline__ void acc_wait(uint64_t* bar, uint32_t parity, int lane) {
+#if VLG_TC_WAIT_MODE == 1
+  if (lane == 0) mbar_wait(bar, parity);
+  __syncwarp();
+#else
+  (void)lane;
+  mbar_wait(bar, parity);
+#endif
+}
+
+struct TcSmem {
+  unsigned char* ring;  // [chain][stage] 16 KB
+  float* XD;            // [m][W][52]: left-end outputs x1, then (after the energy pass) x2 - x1
+  uint8_t* sel;         // [m][role][W] drawn decoder per segment
+  uint16_t* rows;       // [K][W] points of the window that drew decoder k
+  int* cnt;             // [K]
+  WinCtl* ctl;          // [2] item lists, double buffered by window parity
+  float* sw;            // [chain][3 buffers] 576 floats
+  float2* zs;           // W latent points of the window
+  float2* dzs;          // [chain][half][W]
+  float* coef;          // 64
+  float* basis;         // 288
+  float* om;            // 56
+  float* gacc;          // 20
+  float* red;           // 16*20 + 32
+  uint64_t* bars;       // full[2][MAX_STAGES], empty[2][MAX_STAGES], a_ready[2], acc_ready[2], win_ready
+  uint32_t* tmem_base;  // [0] TMEM base address, [1] current work unit
+};
+
+constexpr int CTL_FLOATS = (2 * sizeof(WinCtl) + 3) / 4;
+constexpr int BAR_WORDS = 2 * (4 * MAX_STAGES + 5);
+
+// Fixed-size pieces first, at compile-time offsets from the start of dynamic shared memory (their
+// addresses fold into immediates -- the epilogue code is short of registers), then the window-sized
+// arrays, then the weight rings.
+constexpr int FIX_SW = 0;                                   // 2 chains x 3 buffers x 576
+constexpr int FIX_COEF = FIX_SW + 6 * 576;                  // 64
+constexpr int FIX_BASIS = FIX_COEF + 64;                    // 4 * MAX_NPOLY * MAX_KB
+constexpr int FIX_OM = FIX_BASIS + 4 * MAX_NPOLY * MAX_KB;  // 3 * 2 * MAX_KB + 2
+constexpr int FIX_GACC = FIX_OM + 3 * 2 * MAX_KB + 2;       // 2 * MAX_KB + 2
+constexpr int FIX_RED = FIX_GACC + 2 * MAX_KB + 2;          // 352
+constexpr int FIX_BARS = FIX_RED + 352;                     // BAR_WORDS (8-byte aligned)
+constexpr int FIX_TMEM = FIX_BARS + BAR_WORDS;              // 4
+constexpr int FIX_CTL = FIX_TMEM + 4;                       // CTL_FLOATS
+constexpr int FIX_CNT = FIX_CTL + CTL_FLOATS;               // TC_MAX_K
+constexpr int FIX_FLOATS = (FIX_CNT + TC_MAX_K + 3) / 4 * 4;  // XD starts 16-byte aligned
+static_assert(FIX_BARS % 2 == 0, "mbarriers need 8-byte alignment");
+
+__device__ __forceinline__ TcSmem tc_carve(unsigned char* base, int W, int K, int M, int nst) {
+  TcSmem s;
+  float* f = reinterpret_cast<float*>(base);
+  s.sw = f + FIX_SW;
+  s.coef = f + FIX_COEF;
+  s.basis = f + FIX_BASIS;
+  s.om = f + FIX_OM;
+  s.gacc = f + FIX_GACC;
+  s.red = f + FIX_RED;
+  s.bars = reinterpret_cast<uint64_t*>(f + FIX_BARS);
+  s.tmem_base = reinterpret_cast<uint32_t*>(f + FIX_TMEM);
+  s.ctl = reinterpret_cast<WinCtl*>(f + FIX_CTL);
+  s.cnt = reinterpret_cast<int*>(f + FIX_CNT);
+  f += FIX_FLOATS;
+  s.XD = f; f += M * W * XD_STRIDE;
+  s.zs = reinterpret_cast<float2*>(f); f += 2 * W;
+  s.dzs = reinterpret_cast<float2*>(f); f += 2 * 4 * W;
+  s.sel = reinterpret_cast<uint8_t*>(f); f += TC_MAX_M * 2 * W / 4 + 1;
+  s.rows = reinterpret_cast<uint16_t*>(f);
+  const size_t ring_off = (size_t(reinterpret_cast<unsigned char*>(f) - base) + size_t(K) * W * 2 + 127) / 128 * 128;
+  s.ring = base + ring_off;
+  (void)nst;
+  return s;
+}
+
+}  // namespace
+
+static size_t tc_smem_fixed_bytes(int W, int K, int M) {
+  // everything but the weight rings, in the order of tc_carve (+ alignment slack before the rings)
+  size_t fl = size_t(FIX_FLOATS) + size_t(M) * W * XD_STRIDE + 2 * size_t(W) + 2 * 4 * size_t(W) + TC_MAX_M * 2 * size_t(W) / 4 + 1;
+  return (fl * 4 + size_t(K) * W * 2 + 127) / 128 * 128;
+}
+static int tc_stages(int W, int K, int M) {
+  const long budget = 232448 - long(tc_smem_fixed_bytes(W, K, M));
+  long nst = budget / (2 * STAGE_BYTES);
+  if (nst > MAX_STAGES) nst = MAX_STAGES;
+  return int(nst);
+}
+
+template <bool GRAD, bool F16>
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, int nst, int W) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int M = p.M, K = p.K, T = p.T, n_poly = p.n_poly, Kb = p.Kb;
+  TcSmem s = tc_carve(smem_raw, W, K, M, nst);
+  const int WSEG = W - 1;  // segments per window
+  uint64_t* full = s.bars;                       // [2][MAX_STAGES]
+  uint64_t* empty = s.bars + 2 * MAX_STAGES;     // [2][MAX_STAGES]
+  uint64_t* a_ready = s.bars + 4 * MAX_STAGES;
+  uint64_t* acc_ready = s.bars + 4 * MAX_STAGES + 2;
+  uint64_t* win_ready = s.bars + 4 * MAX_STAGES + 4;
+  const int nwin = (T - 1 + WSEG - 1) / WSEG;
+  // work queue (zeroed by the host before the launch): [0] next unit, [64 + n] chunks done of curve n
+  unsigned int* queue = reinterpret_cast<unsigned int*>(p.workspace);
+  const int unit_steps = p.unit_steps;
+  const int nchunks = (p.steps + unit_steps - 1) / unit_steps;
+  const unsigned int total_units = unsigned(p.N) * unsigned(nchunks);
+
+  if (tid == 0) {
+    for (int i = 0; i < 2 * MAX_STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(&a_ready[0], GROUP_THREADS);
+    mbar_init(&a_ready[1], GROUP_THREADS);
+    mbar_init(&acc_ready[0], 1);
+    mbar_init(&acc_ready[1], 1);
+    mbar_init(win_ready, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(s.tmem_base, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s.tmem_base;
+
+  // Item i of a window (decoder k, rows 128q..128q+127 of k's row list) belongs to chain i & 1.
+  // Per chain the tensor-core ops of a window are: for each of its items F2 F3, then (GRAD) for
+  // each of its items B3 B2.  The item list of window w is published in ctl[w & 1] and
+  // announced through the win_ready mbarrier (phase = w).
+  if (warp < 2) {
+    // ================= weight producer of chain `warp` (TMA bulk copies) =================
+    if (lane == 0) {
+      const int c = warp;
+      uint64_t* fullc = full + c * MAX_STAGES;
+      uint64_t* emptyc = empty + c * MAX_STAGES;
+      unsigned char* ringc = s.ring + c * nst * STAGE_BYTES;
+      int slot = 0;
+      uint32_t ph = 0;
+      for (long w = 0;; ++w) {
+        mbar_wait(win_ready, uint32_t(w & 1));
+        const WinCtl* ctl = &s.ctl[w & 1];
+        const int nit = ctl->nitems;
+        if (nit < 0) break;  // no more work units
+        for (int phase = 0; phase < (GRAD ? 2 : 1); ++phase)
+          for (int i = c; i < nit; i += 2) {
+            const int k = ctl->item[i] & 0xFF;
+            for (int o = 0; o < 2; ++o) {
+              const OpInfo oi = op_info<F16>(phase * 2 + o);
+              const char* src = reinterpret_cast<const char*>(dec_ptr(p.packed, k) + oi.img_off);
+              for (int st = 0; st < oi.nstages; ++st) {
+                mbar_wait(&emptyc[slot], ph ^ 1);
+                mbar_expect_tx(&fullc[slot], STAGE_BYTES);
+                bulk_g2s(ringc + slot * STAGE_BYTES, src + size_t(st) * STAGE_BYTES, STAGE_BYTES, &fullc[slot]);
+                if (++slot == nst) { slot = 0; ph ^= 1; }
+              }
+            }
+          }
+      }
+    }
+  } else if (warp == 2) {
+    // ================= MMA issuer: serves whichever chain is ready =================
+    // The whole warp runs this loop convergently; one elected lane's tcgen05 instructions take effect.
+    {
+      const uint32_t leader = elect_one();
+      int slot[2] = {0, 0}, opi[2] = {0, 0}, nitc[2] = {0, 0};
+      int ops_left[2] = {0, 0};      // ops of the chain's current window still to issue
+      long win[2] = {0, 0};          // next window whose item list the chain has to pick up
+      bool fin[2] = {false, false};
+      uint32_t ph[2] = {0, 0}, ph_a[2] = {0, 0};
+      long long w_full = 0, w_issue = 0;
+      STAT_T0();
+#ifndef VLG_TC_IDLE_NS
+#define VLG_TC_IDLE_NS 0
+#endif
+      bool served = true;
+      while (!(fin[0] && fin[1])) {
+        // back off when nothing was ready: a tight mbarrier.test_wait loop floods the SM's memory
+        // instruction queue and throttles the epilogue warps' loads (seen as lg/mio stalls in ncu)
+        if (!served && VLG_TC_IDLE_NS > 0) __nanosleep(VLG_TC_IDLE_NS);
+        served = false;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          if (fin[c]) continue;
+          if (ops_left[c] == 0) {
+            if (!mbar_test(win_ready, uint32_t(win[c] & 1))) continue;
+            const int nit = s.ctl[win[c] & 1].nitems;
+            if (nit < 0) { fin[c] = true; continue; }
+            nitc[c] = (nit - c + 1) / 2;  // items of this chain in the window
+            ops_left[c] = nitc[c] * (GRAD ? 4 : 2);
+            opi[c] = 0;
+            ++win[c];
+            if (ops_left[c] == 0) continue;
+          }
+          if (!mbar_test(&a_ready[c], ph_a[c])) continue;
+          served = true;
+          ph_a[c] ^= 1;
+          tc_fence_after();
+          // op order inside a window: F2 F3 per item, then B3 B2 per item
+          const int optype = (opi[c] < 2 * nitc[c]) ? (opi[c] & 1) : 2 + ((opi[c] - 2 * nitc[c]) & 1);
+          const OpInfo oi = op_info<F16>(optype);
+          const uint32_t idesc = F16 ? umma_idesc_f16(oi.n) : umma_idesc_tf32(oi.n, 0);
+          const uint32_t chain = tmem + uint32_t(c) * 256u;
+          uint64_t* fullc = full + c * MAX_STAGES;
+          uint64_t* emptyc = empty + c * MAX_STAGES;
+          const unsigned char* ringc = s.ring + c * nst * STAGE_BYTES;
+          for (int st = 0; st < oi.nstages; ++st) {
+            if (!mbar_test(&fullc[slot[c]], ph[c])) { STAT_T0(); mbar_wait(&fullc[slot[c]], ph[c]); STAT_ADD(w_full); }
+            tc_fence_after();
+            const uint32_t sbase = smem_u32(ringc + slot[c] * STAGE_BYTES);
+            const int nk = oi.nk;
+            {
+              STAT_T0();
+              for (int ks = 0; ks < nk; ++ks) {
+                const uint64_t desc =
+                    umma_smem_desc(sbase + uint32_t(ks) * 2u * uint32_t(oi.n) * 16u, uint32_t(oi.n) * 16u, 128u);
+                // fp16 path: item idx of the chain = op / 2 within the forward resp. backward phase
+                const int item_idx = (opi[c] < 2 * nitc[c] ? opi[c] : opi[c] - 2 * nitc[c]) >> 1;
+                const uint32_t a_addr = chain + oi.a_col + (F16 ? uint32_t(item_idx & 1) * 64u : 0u) + uint32_t((st * nk + ks) * 8);
+                if (F16)
+                  umma_f16_ts_elect(chain + oi.d_col, a_addr, desc, idesc, (st | ks) ? 1u : 0u, leader);
+                else
+                  umma_tf32_ts_elect(chain + oi.d_col, a_addr, desc, idesc, (st | ks) ? 1u : 0u, leader);
+              }
+              umma_commit_elect(&emptyc[slot[c]], leader);
+              STAT_ADD(w_issue);
+            }
+            if (++slot[c] == nst) { slot[c] = 0; ph[c] ^= 1; }
+          }
+          umma_commit_elect(&acc_ready[c], leader);
+          ++opi[c];
+          --ops_left[c];
+        }
+      }
+#ifdef VLG_TC_STATS
+      if (lane == 0 && blockIdx.x < 1024) {
+        g_tc_stats[blockIdx.x * 8 + 2] = w_full;
+        g_tc_stats[blockIdx.x * 8 + 3] = clock64() - _t0;
+        g_tc_stats[blockIdx.x * 8 + 5] = w_issue;
+      }
+#endif
+      (void)w_full; (void)w_issue;
+    }
+  } else {
+    // ================= epilogue groups =================
+    const int ew = warp - FIRST_EPI_WARP;       // 0..15
+    const int chain_id = ew >> 3;               // group / chain
+    const int half = (ew >> 2) & 1;             // which 64 of the 128 columns
+    const int row = (warp & 3) * 32 + lane;     // TMEM lane = row of the item
+    const int tg = half * 128 + row;            // 0..255 inside the group
+    const int t512 = chain_id * 256 + tg;       // 0..511 over both groups
+    const uint32_t lane_addr = uint32_t((warp & 3) * 32) << 16;
+    const uint32_t chain = tmem + lane_addr + uint32_t(chain_id) * 256u;
+    const uint32_t colX = chain, colY = chain + 128u;
+    const int col0 = half * 64;                 // this thread's hidden units
+    const int xc0 = half * 32;                  // this thread's output / G columns
+    const int nq = half ? (XD_STRIDE - 32) / 4 : 8;  // float4 groups of this thread's output columns
+    const int bar_id = 1 + chain_id;
+    float* swbuf = s.sw + chain_id * 3 * 576;
+    int swbase = 0;                             // fp16 path: ring position of the window's first stream item
+    int swsel = 0;
+    uint32_t ph_acc = 0;
+    const float coefm = 2.0f / float(M);
+    long long w_acc = 0;
+    long wcount = 0;                            // windows processed by this CTA so far
+    // this CTA's slice of the L2-resident workspace: layer-2 ReLU masks [item][row][4 words], then the
+    // right-end decoder outputs x2 [m][W][52].  (The left-end outputs x1 / the differences stay in shared
+    // memory: with them in L2 too the dE/dx build sits on L2 latency and the kernel runs 2x slower.)
+    const size_t ws_cta = size_t(K + 16) * 512 + size_t(M) * W * XD_STRIDE;  // 32-bit words per CTA
+    uint32_t* maskws = reinterpret_cast<uint32_t*>(p.workspace) + tc_queue_words(p.N) + size_t(blockIdx.x) * ws_cta;
+    float* X1 = s.XD;
+    float* X2 = reinterpret_cast<float*>(maskws + size_t(K + 16) * 512);
+
+    for (int i = t512; i < 4 * n_poly * Kb; i += EPI_THREADS) s.basis[i] = p.basis[i];
+
+    for (;;) {
+      // ---- next work unit: (curve n, steps [step_lo, step_hi)) ----
+      if (t512 == 0) {
+        const unsigned int u = atomicAdd(&queue[0], 1u);
+        s.tmem_base[1] = u;
+        if (u < total_units && u >= unsigned(p.N)) {
+          // a later chunk of a curve: wait until its previous chunk has been written back
+          const unsigned int* flag = &queue[64 + u % unsigned(p.N)];
+          const unsigned int need = u / unsigned(p.N);
+          unsigned int have;
+          do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(have) : "l"(flag) : "memory");
+            if (have < need) __nanosleep(100);
+          } while (have < need);
+        }
+      }
+      named_bar(3, EPI_THREADS);
+      const unsigned int unit = s.tmem_base[1];
+      if (unit >= total_units) break;
+      const int n = int(unit % unsigned(p.N));
+      const int chunk = int(unit / unsigned(p.N));
+      const int step_lo = chunk * unit_steps, step_hi = min(p.steps, step_lo + unit_steps);
+      if (t512 < 2 * Kb) {
+        s.om[t512] = __ldcg(p.omega + size_t(n) * 2 * Kb + t512);
+        if (GRAD) {
+          s.om[2 * MAX_KB + t512] = __ldcg(p.adam_m + size_t(n) * 2 * Kb + t512);
+          s.om[4 * MAX_KB + t512] = __ldcg(p.adam_v + size_t(n) * 2 * Kb + t512);
+        }
+      }
+      const float2 pa = make_float2(p.a[2 * n], p.a[2 * n + 1]);
+      const float2 pb = make_float2(p.b[2 * n], p.b[2 * n + 1]);
+      named_bar(3, EPI_THREADS);
+
+      for (int step = step_lo; step < step_hi; ++step) {
+        if (t512 < 8 * n_poly) {
+          const int r = t512 >> 1, d = t512 & 1;
+          float acc = 0.f;
+          for (int k = 0; k < Kb; ++k) acc = fmaf(s.basis[r * Kb + k], s.om[2 * k + d], acc);
+          s.coef[t512] = acc;
+        }
+        if (t512 < 2 * MAX_KB) s.gacc[t512] = 0.f;
+        float e_tot = 0.f, l_tot = 0.f;  // meaningful in t512 == 0
+        named_bar(3, EPI_THREADS);
+
+        for (int win = 0; win < nwin; ++win, ++wcount) {
+          const int seg0 = win * WSEG;
+          const int nseg = min(WSEG, T - 1 - seg0);
+          WinCtl* ctl = &s.ctl[wcount & 1];
+          // ---- window setup: points, draws, accumulators ----
+          if (t512 < W) {
+            const int pt = t512;
+            const int ti = min(seg0 + pt, T - 1);
+            s.zs[pt] = spline_point(p.t[ti], n_poly, s.coef, pa, pb);
+            if (p.draws != nullptr) {
+              for (int m = 0; m < M; ++m)
+                for (int role = 0; role < 2; ++role) {
+                  uint8_t v = 255;
+                  if (pt < nseg)
+                    v = p.draws[(((size_t(n) * p.steps + step) * M + m) * 2 + role) * size_t(T - 1) + seg0 + pt];
+                  s.sel[(m * 2 + role) * W + pt] = v;
+                }
+            } else {
+              uint32_t d[4] = {255u, 255u, 255u, 255u};
+              if (pt < nseg)
+                counter_draws4(p.seed, uint32_t(p.curve_id0 + n), uint32_t(p.step0 + step), uint32_t(seg0 + pt), 0u,
+                               uint32_t(K), d);
+              for (int q = 0; q < 4; ++q) {
+                const int m = q >> 1;
+                if (m < M) s.sel[(m * 2 + (q & 1)) * W + pt] = uint8_t(d[q]);
+              }
+            }
+          }
+          for (int i = t512; i < 4 * W; i += EPI_THREADS) s.dzs[i] = make_float2(0.f, 0.f);
+          if (t512 < K) s.cnt[t512] = 0;
+          named_bar(3, EPI_THREADS);
+          // ---- per-decoder row lists ----
+          if (t512 <= nseg) {
+            const int pt = t512;
+            int cand[2 * TC_MAX_M];
+            int nc = 0;
+            for (int m = 0; m < M; ++m) {
+              if (pt < nseg) cand[nc++] = s.sel[(m * 2 + 0) * W + pt];
+              if (pt >= 1) cand[nc++] = s.sel[(m * 2 + 1) * W + pt - 1];
+            }
+            for (int i = 0; i < nc; ++i) {
+              bool dup = false;
+              for (int j = 0; j < i; ++j) dup |= (cand[j] == cand[i]);
+              if (!dup) {
+                const int slot = atomicAdd(&s.cnt[cand[i]], 1);
+                s.rows[cand[i] * W + slot] = uint16_t(pt);
+              }
+            }
+          }
+          named_bar(3, EPI_THREADS);
+          if (t512 == 0) {
+            int ni = 0;
+            for (int k = 0; k < K; ++k)
+              for (int q = 0; q * 128 < s.cnt[k]; ++q) ctl->item[ni++] = uint16_t(k | (q << 8));
+            ctl->nitems = ni;
+            __threadfence_block();
+            mbar_arrive(win_ready);
+          }
+          named_bar(3, EPI_THREADS);
+          const int nitems = ctl->nitems;
+          // small weights (W1, b1, b2, b3) of this group's first item
+          if (!F16 && chain_id < nitems && tg < 144)
+            cp_async16(swbuf + swsel * 576 + tg * 4, dec_ptr(p.packed, ctl->item[chain_id] & 0xFF) + tg * 4);
+
+          // ---------------------------------------------------------------------------------------------
+          // fp16 path: the items of a chain form a software pipeline.  Per window the chain's "stream" is its
+          // forward items followed by its backward items; small weights of stream item j sit in buffer
+          // (swbase + j) % 3 and are prefetched two items ahead, right after the one group barrier per item.
+          // ---------------------------------------------------------------------------------------------
+          struct Item { int k, pt, it; bool active, wact; };
+          const int nloc = nitems > chain_id ? (nitems - chain_id + 1) / 2 : 0;   // items of this chain
+          const int nstream = GRAD ? 2 * nloc : nloc;
+          auto get_item = [&](int li) {
+            Item r;
+            r.it = chain_id + 2 * li;
+            const int e = ctl->item[r.it];
+            r.k = e & 0xFF;
+            const int q0 = (e >> 8) * 128, c = s.cnt[r.k];
+            r.active = q0 + row < c;
+            // tcgen05.ld/st are warp-collective: a warp takes part as soon as one of its 32 rows is in use
+            r.wact = q0 + (warp & 3) * 32 < c;
+            r.pt = r.active ? s.rows[r.k * W + q0 + row] : 0;
+            return r;
+          };
+          auto sw_of = [&](int j) { return swbuf + ((swbase + j) % 3) * 576; };
+          auto prefetch_sw = [&](int j) {
+            if (j < nstream && tg < 144) {
+              const int li = j < nloc ? j : j - nloc;
+              cp_async16(sw_of(j) + tg * 4, dec_ptr(p.packed, ctl->item[chain_id + 2 * li] & 0xFF) + tg * 4);
+            }
+          };
+          // layer 1 (CUDA cores, fp32) -> fp16 pairs in operand buffer `buf`
+          auto f16_layer1 = [&](const Item& im, const float* sw, int buf) {
+            const float2 z = s.zs[im.pt];
+            const float2 zx2 = make_float2(z.x, z.x), zy2 = make_float2(z.y, z.y);
+            if (im.wact) {
+              uint32_t v[32];
+#pragma unroll
+              for (int j = 0; j < 64; j += 4) {
+                const int c = col0 + j;
+                const float4 wx = *reinterpret_cast<const float4*>(sw + OFF_W1X + c);
+                const float4 wy = *reinterpret_cast<const float4*>(sw + OFF_W1Y + c);
+                const float4 bb = *reinterpret_cast<const float4*>(sw + OFF_B1 + c);
+                const float2 h0 = __ffma2_rn(make_float2(wy.x, wy.y), zy2, __ffma2_rn(make_float2(wx.x, wx.y), zx2, make_float2(bb.x, bb.y)));
+                const float2 h1 = __ffma2_rn(make_float2(wy.z, wy.w), zy2, __ffma2_rn(make_float2(wx.z, wx.w), zx2, make_float2(bb.z, bb.w)));
+                v[j >> 1] = pack_relu_h2(h0.x, h0.y);
+                v[(j >> 1) + 1] = pack_relu_h2(h1.x, h1.y);
+              }
+              tmem_st32(colX + buf * 64 + half * 32, v);
+            }
+            tmem_wait_st();
+            tc_fence_before();
+          };
+          // D2 (Y) -> relu(+b2) -> fp16 pairs in operand buffer `buf` (over the dead layer-1 output), mask bits
+          auto f16_ef2 = [&](const Item& im, const float* sw, int buf) {
+            if (im.wact) {
+              uint32_t bits[2];
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh) {
+                uint32_t v[32];
+                tmem_ld32_sync(colY + col0 + 32 * hh, v);
+                uint32_t bb = 0;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  const float4 b0 = *reinterpret_cast<const float4*>(sw + OFF_B2 + col0 + 32 * hh + j);
+                  const float2 p0 = __fadd2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), make_float2(b0.x, b0.y));
+                  const float2 p1 = __fadd2_rn(make_float2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])), make_float2(b0.z, b0.w));
+                  if (p0.x > 0.f) bb |= 1u << j;
+                  if (p0.y > 0.f) bb |= 2u << j;
+                  if (p1.x > 0.f) bb |= 4u << j;
+                  if (p1.y > 0.f) bb |= 8u << j;
+                  const uint32_t a0 = pack_relu_h2(p0.x, p0.y), a1 = pack_relu_h2(p1.x, p1.y);
+                  v[j >> 1] = a0;   // slots j/2, j/2+1 <= j were consumed already
+                  v[(j >> 1) + 1] = a1;
+                }
+                bits[hh] = bb;
+                tmem_st16(colX + buf * 64 + half * 32 + 16 * hh, reinterpret_cast<uint32_t(&)[16]>(v));
+              }
+              if (GRAD && im.active) *reinterpret_cast<uint2*>(maskws + (im.it * 128 + row) * 4 + half * 2) = make_uint2(bits[0], bits[1]);
+            }
+            tmem_wait_st();
+            tc_fence_before();
+          };
+          auto f16_store_x = [&](const Item& im, const float (&x)[32]) {
+            for (int m = 0; m < (im.active ? M : 0); ++m) {
+              // role 0: this point is the left end of its segment; role 1: right end of the previous one
+              if (s.sel[(m * 2 + 0) * W + im.pt] == im.k) {
+                float4* d = reinterpret_cast<float4*>(X1 + (m * W + im.pt) * XD_STRIDE + xc0);
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                  if (q < nq) d[q] = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+              }
+              if (im.pt >= 1 && s.sel[(m * 2 + 1) * W + im.pt - 1] == im.k) {
+                float4* d = reinterpret_cast<float4*>(X2 + (m * W + im.pt - 1) * XD_STRIDE + xc0);
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                  if (q < nq) d[q] = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+              }
+            }
+          };
+
+          if (F16 && nloc > 0) {
+            // =============================== forward (fp16, pipelined) ===============================
+            prefetch_sw(0);
+            prefetch_sw(1);
+            cp_async_wait_all();
+            named_bar(bar_id, GROUP_THREADS);
+            Item cur = get_item(0);
+            f16_layer1(cur, sw_of(0), 0);
+            mbar_arrive(&a_ready[chain_id]);                      // F2(0)
+            for (int li = 0; li < nloc; ++li) {
+              const float* sw = sw_of(li);
+              acc_wait(&acc_ready[chain_id], ph_acc, lane);       // D2(li)
+              ph_acc ^= 1;
+              tc_fence_after();
+              f16_ef2(cur, sw, li & 1);
+              mbar_arrive(&a_ready[chain_id]);                    // F3(li)
+              // the one group barrier of the item: everybody is past E-F3(li-1), the small weights of
+              // item li+1 have landed; the buffer of item li-1 is free for item li+2
+              cp_async_wait_all();
+              named_bar(bar_id, GROUP_THREADS);
+              prefetch_sw(li + 2);
+              if (li + 1 < nloc) {
+                const Item nxt = get_item(li + 1);
+                f16_layer1(nxt, sw_of(li + 1), (li + 1) & 1);     // overlaps F3(li)
+              }
+              acc_wait(&acc_ready[chain_id], ph_acc, lane);       // D3(li) in Y[0:64]
+              ph_acc ^= 1;
+              tc_fence_after();
+              float x[32];
+              if (cur.wact) {
+                uint32_t xv[32];
+                tmem_ld32_sync(colY + xc0, xv);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  const float4 bb = *reinterpret_cast<const float4*>(sw + OFF_B3 + xc0 + j);
+                  x[j] = __uint_as_float(xv[j]) + bb.x;
+                  x[j + 1] = __uint_as_float(xv[j + 1]) + bb.y;
+                  x[j + 2] = __uint_as_float(xv[j + 2]) + bb.z;
+                  x[j + 3] = __uint_as_float(xv[j + 3]) + bb.w;
+                }
+              }
+              tc_fence_before();
+              if (li + 1 < nloc) mbar_arrive(&a_ready[chain_id]); // F2(li+1): its operand and Y are both ready
+              if (cur.wact) f16_store_x(cur, x);                  // overlaps F2(li+1)
+              if (li + 1 < nloc) cur = get_item(li + 1);          // (re-read: cheaper than carrying it in registers)
+            }
+          }
+          // =============================== forward ===============================
+          if (!F16)
+          for (int it = chain_id; it < nitems; it += 2) {
+            const int k = ctl->item[it] & 0xFF, q0 = (ctl->item[it] >> 8) * 128;
+            const bool active = q0 + row < s.cnt[k];
+            // tcgen05.ld/st are warp-collective (.sync.aligned): a warp takes part as soon as one of
+            // its 32 rows is in use; unused lanes compute on point 0 and store nothing
+            const bool wact = q0 + (warp & 3) * 32 < s.cnt[k];
+            const int pt = active ? s.rows[k * W + q0 + row] : 0;
+            // small weights of decoder k were prefetched into swbuf[swsel]; prefetch the next item's
+            cp_async_wait_all();
+            named_bar(bar_id, GROUP_THREADS);
+            const float* sw = swbuf + swsel * 576;
+            {
+              int nx = it + 2;
+              if (nx >= nitems) nx = GRAD ? chain_id : -1;
+              if (nx >= 0 && tg < 144)
+                cp_async16(swbuf + (swsel ^ 1) * 576 + tg * 4, dec_ptr(p.packed, ctl->item[nx] & 0xFF) + tg * 4);
+            }
+            swsel ^= 1;
+            const float2 z = s.zs[pt];
+            const float2 zx2 = make_float2(z.x, z.x), zy2 = make_float2(z.y, z.y);
+            // layer 1 (CUDA cores, fp32) -> A1 in X[col0 : col0+64]  (fp16: pairs in X[32 half : +32])
+            if (F16) {
+              if (wact) {
+                uint32_t v[32];
+#pragma unroll
+                for (int j = 0; j < 64; j += 4) {
+                  const int c = col0 + j;
+                  const float4 wx = *reinterpret_cast<const float4*>(sw + OFF_W1X + c);
+                  const float4 wy = *reinterpret_cast<const float4*>(sw + OFF_W1Y + c);
+                  const float4 bb = *reinterpret_cast<const float4*>(sw + OFF_B1 + c);
+                  const float2 h0 = __ffma2_rn(make_float2(wy.x, wy.y), zy2,
+                                               __ffma2_rn(make_float2(wx.x, wx.y), zx2, make_float2(bb.x, bb.y)));
+                  const float2 h1 = __ffma2_rn(make_float2(wy.z, wy.w), zy2,
+                                               __ffma2_rn(make_float2(wx.z, wx.w), zx2, make_float2(bb.z, bb.w)));
+                  v[j >> 1] = pack_relu_h2(h0.x, h0.y);
+                  v[(j >> 1) + 1] = pack_relu_h2(h1.x, h1.y);
+                }
+                tmem_st32(colX + half * 32, v);
+              }
+            } else if (wact) {
+#pragma unroll
+              for (int c0 = 0; c0 < 64; c0 += 32) {
+                uint32_t v[32];
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  const int c = col0 + c0 + j;
+                  const float4 wx = *reinterpret_cast<const float4*>(sw + OFF_W1X + c);
+                  const float4 wy = *reinterpret_cast<const float4*>(sw + OFF_W1Y + c);
+                  const float4 bb = *reinterpret_cast<const float4*>(sw + OFF_B1 + c);
+                  const float2 h0 = __ffma2_rn(make_float2(wy.x, wy.y), zy2,
+                                               __ffma2_rn(make_float2(wx.x, wx.y), zx2, make_float2(bb.x, bb.y)));
+                  const float2 h1 = __ffma2_rn(make_float2(wy.z, wy.w), zy2,
+                                               __ffma2_rn(make_float2(wx.z, wx.w), zx2, make_float2(bb.z, bb.w)));
+                  v[j] = relu_tf32(h0.x);
+                  v[j + 1] = relu_tf32(h0.y);
+                  v[j + 2] = relu_tf32(h1.x);
+                  v[j + 3] = relu_tf32(h1.y);
+                }
+                tmem_st32(colX + col0 + c0, v);
+              }
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(&a_ready[chain_id]);
+            // layer 2 epilogue: D2 (Y) -> relu(+b2) -> A2 (Y, in place), mask bits
+            { STAT_T0(); acc_wait(&acc_ready[chain_id], ph_acc, lane); STAT_ADD(w_acc); }
+            ph_acc ^= 1;
+            tc_fence_after();
+            if (wact) {
+              // two passes of 32 columns: one live 32-register tile instead of two (no spills)
+              uint32_t bits[2];
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh) {
+                uint32_t v[32];
+                tmem_ld32_sync(colY + col0 + 32 * hh, v);
+                uint32_t bb = 0;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  const float4 b0 = *reinterpret_cast<const float4*>(sw + OFF_B2 + col0 + 32 * hh + j);
+                  const float2 p0 = __fadd2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), make_float2(b0.x, b0.y));
+                  const float2 p1 = __fadd2_rn(make_float2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])), make_float2(b0.z, b0.w));
+                  if (p0.x > 0.f) bb |= 1u << j;
+                  if (p0.y > 0.f) bb |= 2u << j;
+                  if (p1.x > 0.f) bb |= 4u << j;
+                  if (p1.y > 0.f) bb |= 8u << j;
+                  if (F16) {
+                    // pairs go to v[0:16] (slots j/2, j/2+1 <= j were consumed already)
+                    const uint32_t a0 = pack_relu_h2(p0.x, p0.y), a1 = pack_relu_h2(p1.x, p1.y);
+                    v[j >> 1] = a0;
+                    v[(j >> 1) + 1] = a1;
+                  } else {
+                    v[j] = relu_tf32(p0.x); v[j + 1] = relu_tf32(p0.y); v[j + 2] = relu_tf32(p1.x); v[j + 3] = relu_tf32(p1.y);
+                  }
+                }
+                bits[hh] = bb;
+                if (F16)
+                  tmem_st16(colX + half * 32 + 16 * hh, reinterpret_cast<uint32_t(&)[16]>(v));
+                else
+                  tmem_st32(colY + col0 + 32 * hh, v);
+              }
+              if (GRAD && active) *reinterpret_cast<uint2*>(maskws + (it * 128 + row) * 4 + half * 2) = make_uint2(bits[0], bits[1]);
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(&a_ready[chain_id]);
+            // layer 3 epilogue: D3 (X[0:64]) + b3 -> the slots of this point that drew decoder k
+            { STAT_T0(); acc_wait(&acc_ready[chain_id], ph_acc, lane); STAT_ADD(w_acc); }
+            ph_acc ^= 1;
+            tc_fence_after();
+            if (wact) {
+              uint32_t xv[32];
+              tmem_ld32_sync(colX + (F16 ? 64 : 0) + xc0, xv);
+              float x[32];
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 bb = *reinterpret_cast<const float4*>(sw + OFF_B3 + xc0 + j);
+                x[j] = __uint_as_float(xv[j]) + bb.x;
+                x[j + 1] = __uint_as_float(xv[j + 1]) + bb.y;
+                x[j + 2] = __uint_as_float(xv[j + 2]) + bb.z;
+                x[j + 3] = __uint_as_float(xv[j + 3]) + bb.w;
+              }
+              for (int m = 0; m < (active ? M : 0); ++m) {
+                // role 0: this point is the left end of its segment; role 1: right end of the previous one
+                if (s.sel[(m * 2 + 0) * W + pt] == k) {
+                  float4* d = reinterpret_cast<float4*>(X1 + (m * W + pt) * XD_STRIDE + xc0);
+#pragma unroll
+                  for (int q = 0; q < 8; ++q)
+                    if (q < nq) d[q] = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+                }
+                if (pt >= 1 && s.sel[(m * 2 + 1) * W + pt - 1] == k) {
+                  float4* d = reinterpret_cast<float4*>(X2 + (m * W + pt - 1) * XD_STRIDE + xc0);
+#pragma unroll
+                  for (int q = 0; q < 8; ++q)
+                    if (q < nq) d[q] = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+                }
+              }
+            }
+          }
+          named_bar(3, EPI_THREADS);
+
+          // ======================= x2 - x1 and the energy =======================
+          if (GRAD) {
+            // The valid rows of one MC sample are contiguous in both buffers: a flat, fully coalesced pass
+            // over 16-byte pieces (x2 from L2, x1 from shared memory, the difference back in place), four
+            // independent pieces per thread in flight.  The energy is the plain sum of squares, in a fixed
+            // order (deterministic).
+            float e = 0.f;
+            const int n4 = nseg * (XD_STRIDE / 4);
+            for (int m = 0; m < M; ++m) {
+              const float4* x2 = reinterpret_cast<const float4*>(X2 + m * W * XD_STRIDE);
+              float4* x1 = reinterpret_cast<float4*>(X1 + m * W * XD_STRIDE);
+              for (int i0 = t512; i0 < n4; i0 += 4 * EPI_THREADS) {
+                float4 v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const int i = i0 + j * EPI_THREADS;
+                  v[j] = i < n4 ? __ldcg(x2 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const int i = i0 + j * EPI_THREADS;
+                  if (i < n4) {
+                    const float4 u = x1[i];
+                    const float4 a = make_float4(v[j].x - u.x, v[j].y - u.y, v[j].z - u.z, v[j].w - u.w);
+                    x1[i] = a;
+                    e = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(a.z, a.z, fmaf(a.w, a.w, e))));
+                  }
+                }
+              }
+            }
+            e = warp_sum(e);
+            if (lane == 0) s.red[320 + ew] = e;
+          } else {
+            // forward-only kernel (also reports the polyline length, a sum of per-segment norms): 16 lanes
+            // per (m, segment) entry, one 16-byte piece each; six entries per lane in flight.
+            float e = 0.f, l = 0.f;
+            const int sub = lane & 15;
+            constexpr int NV = XD_STRIDE / 4;   // 13 float4 per row
+            constexpr int UNR = 6;
+            const int nent = M * W;
+            for (int base = ew * 2 + (lane >> 4); base < nent; base += 32 * UNR) {
+              float4 v[UNR];
+#pragma unroll
+              for (int j = 0; j < UNR; ++j) {
+                const int ent = base + 32 * j;
+                const bool ok = ent < nent && (ent % W) < nseg && sub < NV;
+                v[j] = ok ? __ldcg(reinterpret_cast<const float4*>(X2 + ent * XD_STRIDE) + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+#pragma unroll
+              for (int j = 0; j < UNR; ++j) {
+                const int ent = base + 32 * j;
+                const bool ok = ent < nent && (ent % W) < nseg && sub < NV;
+                float q = 0.f;
+                if (ok) {
+                  float4* d0 = reinterpret_cast<float4*>(X1 + ent * XD_STRIDE) + sub;
+                  const float4 u = *d0;
+                  const float4 a = make_float4(v[j].x - u.x, v[j].y - u.y, v[j].z - u.z, v[j].w - u.w);
+                  *d0 = a;
+                  q = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(a.z, a.z, a.w * a.w)));
+                }
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+                if (sub == 0) { e += q; l += sqrtf(q); }
+              }
+            }
+            e = warp_sum(e);
+            l = warp_sum(l);
+            if (lane == 0) { s.red[320 + ew] = e; s.red[336 + ew] = l; }
+          }
+          if (GRAD) named_bar(3, EPI_THREADS);  // the differences are read by other threads below
+
+          if (GRAD && F16 && nloc > 0) {
+            // =============================== backward (fp16, pipelined) ===============================
+            auto load_bits = [&](const Item& im) {
+              uint2 b = make_uint2(0u, 0u);
+              if (im.active) b = *reinterpret_cast<const uint2*>(maskws + (im.it * 128 + row) * 4 + half * 2);
+              return b;
+            };
+            // G = dE/dx_k (this point, this thread's 32 output columns), scaled, as fp16 pairs in buffer `buf`
+            auto f16_g = [&](const Item& im, int buf) {
+              if (im.wact) {
+                float g[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) g[j] = 0.f;
+                for (int m = 0; m < (im.active ? M : 0); ++m) {
+                  if (im.pt >= 1 && s.sel[(m * 2 + 1) * W + im.pt - 1] == im.k) {
+                    const float4* d = reinterpret_cast<const float4*>(X1 + (m * W + im.pt - 1) * XD_STRIDE + xc0);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                      if (q < nq) {
+                        const float4 v = d[q];
+                        g[4 * q] += v.x; g[4 * q + 1] += v.y; g[4 * q + 2] += v.z; g[4 * q + 3] += v.w;
+                      }
+                  }
+                  if (s.sel[(m * 2 + 0) * W + im.pt] == im.k) {
+                    const float4* d = reinterpret_cast<const float4*>(X1 + (m * W + im.pt) * XD_STRIDE + xc0);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                      if (q < nq) {
+                        const float4 v = d[q];
+                        g[4 * q] -= v.x; g[4 * q + 1] -= v.y; g[4 * q + 2] -= v.z; g[4 * q + 3] -= v.w;
+                      }
+                  }
+                }
+                uint32_t v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = pack_h2((coefm * F16_GRAD_SCALE) * g[2 * j], (coefm * F16_GRAD_SCALE) * g[2 * j + 1]);
+                tmem_st16(colX + buf * 64 + half * 16, v);
+              }
+              tmem_wait_st();
+              tc_fence_before();
+            };
+            Item cur = get_item(0);
+            uint2 bits = load_bits(cur);
+            f16_g(cur, 0);
+            mbar_arrive(&a_ready[chain_id]);                      // B3(0)
+            for (int li = 0; li < nloc; ++li) {
+              const float* sw = sw_of(nloc + li);
+              acc_wait(&acc_ready[chain_id], ph_acc, lane);       // D4(li) in Y
+              ph_acc ^= 1;
+              tc_fence_after();
+              if (cur.wact) {
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                  uint32_t v[32];
+                  tmem_ld32_sync(colY + col0 + 32 * hh, v);
+                  const uint32_t mb = hh ? bits.y : bits.x;
+#pragma unroll
+                  for (int j = 0; j < 32; j += 2) {
+                    const float a0 = ((mb >> j) & 1u) ? __uint_as_float(v[j]) : 0.f;
+                    const float a1 = ((mb >> (j + 1)) & 1u) ? __uint_as_float(v[j + 1]) : 0.f;
+                    v[j >> 1] = pack_h2(a0, a1);   // j/2 <= j: slot already consumed
+                  }
+                  tmem_st16(colX + (li & 1) * 64 + half * 32 + 16 * hh, reinterpret_cast<uint32_t(&)[16]>(v));
+                }
+              }
+              tmem_wait_st();
+              tc_fence_before();
+              mbar_arrive(&a_ready[chain_id]);                    // B2(li)
+              cp_async_wait_all();
+              named_bar(bar_id, GROUP_THREADS);
+              prefetch_sw(nloc + li + 2);
+              if (li + 1 < nloc) {
+                const Item nxt = get_item(li + 1);
+                f16_g(nxt, (li + 1) & 1);                         // overlaps B2(li)
+              }
+              acc_wait(&acc_ready[chain_id], ph_acc, lane);       // D5(li) in Y
+              ph_acc ^= 1;
+              tc_fence_after();
+              if (cur.wact) {
+                const float2 z = s.zs[cur.pt];
+                const float2 zx2 = make_float2(z.x, z.x), zy2 = make_float2(z.y, z.y);
+                float2 ax = make_float2(0.f, 0.f), ay = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                  uint32_t v[32];
+                  tmem_ld32_sync(colY + col0 + 32 * hh, v);
+#pragma unroll
+                  for (int j = 0; j < 32; j += 2) {
+                    const int c = col0 + 32 * hh + j;
+                    const float2 wx = *reinterpret_cast<const float2*>(sw + OFF_W1X + c);
+                    const float2 wy = *reinterpret_cast<const float2*>(sw + OFF_W1Y + c);
+                    const float2 bb = *reinterpret_cast<const float2*>(sw + OFF_B1 + c);
+                    const float2 h = __ffma2_rn(wy, zy2, __ffma2_rn(wx, zx2, bb));
+                    const float2 dh = make_float2(h.x > 0.f ? __uint_as_float(v[j]) : 0.f, h.y > 0.f ? __uint_as_float(v[j + 1]) : 0.f);
+                    ax = __ffma2_rn(dh, wx, ax);
+                    ay = __ffma2_rn(dh, wy, ay);
+                  }
+                }
+                tc_fence_before();
+                if (li + 1 < nloc) mbar_arrive(&a_ready[chain_id]);   // B3(li+1): Y has been read, dE/dx is in place
+                // a point occurs at most once per item and the items of a chain run in order:
+                // plain read-modify-write, deterministic
+                if (cur.active) {
+                  float2* dzp = &s.dzs[(chain_id * 2 + half) * W + cur.pt];
+                  float2 acc = *dzp;
+                  acc.x += (ax.x + ax.y) * (1.f / F16_GRAD_SCALE);
+                  acc.y += (ay.x + ay.y) * (1.f / F16_GRAD_SCALE);
+                  *dzp = acc;
+                }
+              } else {
+                tc_fence_before();
+                if (li + 1 < nloc) mbar_arrive(&a_ready[chain_id]);
+              }
+              if (li + 1 < nloc) {
+                cur = get_item(li + 1);
+                bits = load_bits(cur);                            // L2 round trip overlaps B3(li+1)
+              }
+            }
+          }
+          if (F16) swbase = (swbase + nstream) % 3;
+          if (GRAD && !F16) {
+            // =============================== backward ===============================
+            for (int it = chain_id; it < nitems; it += 2) {
+              const int k = ctl->item[it] & 0xFF, q0 = (ctl->item[it] >> 8) * 128;
+              const bool active = q0 + row < s.cnt[k];
+              const bool wact = q0 + (warp & 3) * 32 < s.cnt[k];
+              const int pt = active ? s.rows[k * W + q0 + row] : 0;
+              cp_async_wait_all();
+              named_bar(bar_id, GROUP_THREADS);
+              const float* sw = swbuf + swsel * 576;
+              {
+                const int nx = it + 2;
+                if (nx < nitems && tg < 144)
+                  cp_async16(swbuf + (swsel ^ 1) * 576 + tg * 4, dec_ptr(p.packed, ctl->item[nx] & 0xFF) + tg * 4);
+              }
+              swsel ^= 1;
+              const float2 z = s.zs[pt];
+              const float2 zx2 = make_float2(z.x, z.x), zy2 = make_float2(z.y, z.y);
+              // mask words for E-B3 (L2 round trip overlaps the G build and the first MMA)
+              uint2 bits = make_uint2(0u, 0u);
+              if (active) bits = *reinterpret_cast<const uint2*>(maskws + (it * 128 + row) * 4 + half * 2);
+              // G = dE/dx_k (this point), columns xc0 .. xc0+31 -> X[xc0 : xc0+32]
+              if (wact) {
+                float g[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) g[j] = 0.f;
+                for (int m = 0; m < (active ? M : 0); ++m) {
+                  if (pt >= 1 && s.sel[(m * 2 + 1) * W + pt - 1] == k) {
+                    const float4* d = reinterpret_cast<const float4*>(X1 + (m * W + pt - 1) * XD_STRIDE + xc0);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                      if (q < nq) {
+                        const float4 v = d[q];
+                        g[4 * q] += v.x; g[4 * q + 1] += v.y; g[4 * q + 2] += v.z; g[4 * q + 3] += v.w;
+                      }
+                  }
+                  if (s.sel[(m * 2 + 0) * W + pt] == k) {
+                    const float4* d = reinterpret_cast<const float4*>(X1 + (m * W + pt) * XD_STRIDE + xc0);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                      if (q < nq) {
+                        const float4 v = d[q];
+                        g[4 * q] -= v.x; g[4 * q + 1] -= v.y; g[4 * q + 2] -= v.z; g[4 * q + 3] -= v.w;
+                      }
+                  }
+                }
+                if (F16) {
+                  uint32_t v[16];
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) v[j] = pack_h2((coefm * F16_GRAD_SCALE) * g[2 * j], (coefm * F16_GRAD_SCALE) * g[2 * j + 1]);
+                  tmem_st16(colX + half * 16, v);
+                } else {
+                  uint32_t v[32];
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) v[j] = tf32_round_bits(__float_as_uint(coefm * g[j]));
+                  tmem_st32(colX + xc0, v);
+                }
+              }
+              tmem_wait_st();
+              tc_fence_before();
+              mbar_arrive(&a_ready[chain_id]);
+              // dh2 = (G W3) * mask2 -> A4 (Y, in place)
+              { STAT_T0(); acc_wait(&acc_ready[chain_id], ph_acc, lane); STAT_ADD(w_acc); }
+              ph_acc ^= 1;
+              tc_fence_after();
+              if (wact) {
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                  uint32_t v[32];
+                  tmem_ld32_sync(colY + col0 + 32 * hh, v);
+                  const uint32_t mb = hh ? bits.y : bits.x;
+                  if (F16) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) {
+                      const float a0 = ((mb >> j) & 1u) ? __uint_as_float(v[j]) : 0.f;
+                      const float a1 = ((mb >> (j + 1)) & 1u) ? __uint_as_float(v[j + 1]) : 0.f;
+                      v[j >> 1] = pack_h2(a0, a1);   // j/2 <= j: slot already consumed
+                    }
+                    tmem_st16(colX + half * 32 + 16 * hh, reinterpret_cast<uint32_t(&)[16]>(v));
+                  } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = ((mb >> j) & 1u) ? tf32_round_bits(v[j]) : 0u;
+                    tmem_st32(colY + col0 + 32 * hh, v);
+                  }
+                }
+              }
+              tmem_wait_st();
+              tc_fence_before();
+              mbar_arrive(&a_ready[chain_id]);
+              // dh1 = (dh2 W2) * mask1 (recomputed); dz[point] += dh1 W1 over this thread's 64 hidden units
+              { STAT_T0(); acc_wait(&acc_ready[chain_id], ph_acc, lane); STAT_ADD(w_acc); }
+              ph_acc ^= 1;
+              tc_fence_after();
+              if (wact) {
+                float2 ax = make_float2(0.f, 0.f), ay = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                  uint32_t v[32];
+                  tmem_ld32_sync((F16 ? colY : colX) + col0 + 32 * hh, v);
+#pragma unroll
+                  for (int j = 0; j < 32; j += 2) {
+                    const int c = col0 + 32 * hh + j;
+                    const float2 wx = *reinterpret_cast<const float2*>(sw + OFF_W1X + c);
+                    const float2 wy = *reinterpret_cast<const float2*>(sw + OFF_W1Y + c);
+                    const float2 bb = *reinterpret_cast<const float2*>(sw + OFF_B1 + c);
+                    const float2 h = __ffma2_rn(wy, zy2, __ffma2_rn(wx, zx2, bb));
+                    const float2 dh = make_float2(h.x > 0.f ? __uint_as_float(v[j]) : 0.f, h.y > 0.f ? __uint_as_float(v[j + 1]) : 0.f);
+                    ax = __ffma2_rn(dh, wx, ax);
+                    ay = __ffma2_rn(dh, wy, ay);
+                  }
+                }
+                // a point occurs at most once per item and the items of a chain run in order:
+                // plain read-modify-write, deterministic
+                if (active) {
+                  float2* dzp = &s.dzs[(chain_id * 2 + half) * W + pt];
+                  float2 acc = *dzp;
+                  constexpr float unscale = F16 ? 1.f / F16_GRAD_SCALE : 1.f;
+                  acc.x += (ax.x + ax.y) * unscale;
+                  acc.y += (ay.x + ay.y) * unscale;
+                  *dzp = acc;
+                }
+              }
+            }
+          }
+          named_bar(3, EPI_THREADS);
+          // ---- d(omega) += P^T dz over the points of the window, energy partials ----
+          if (GRAD) {
+            // all 512 epilogue threads, one point each (W <= 512); threads beyond the window add zeros
+            const int pt = t512;
+            float P[MAX_KB];
+            float dx = 0.f, dy = 0.f;
+            if (pt < W) {
+              design_row(p.t[min(seg0 + pt, T - 1)], n_poly, Kb, s.basis, P);
+              const float2 d0 = s.dzs[pt], d1 = s.dzs[W + pt], d2 = s.dzs[2 * W + pt], d3 = s.dzs[3 * W + pt];
+              dx = (d0.x + d1.x) + (d2.x + d3.x);
+              dy = (d0.y + d1.y) + (d2.y + d3.y);
+            } else {
+#pragma unroll
+              for (int k = 0; k < MAX_KB; ++k) P[k] = 0.f;
+            }
+#pragma unroll
+            for (int k = 0; k < MAX_KB; ++k)
+              if (k < Kb) {
+                const float cx = warp_sum(P[k] * dx), cy = warp_sum(P[k] * dy);
+                if (lane == 0) { s.red[ew * 20 + 2 * k] = cx; s.red[ew * 20 + 2 * k + 1] = cy; }
+              }
+          }
+          if (t512 == 0) {
+            float ee = 0.f, ll = 0.f;
+            for (int w = 0; w < 16; ++w) { ee += s.red[320 + w]; ll += s.red[336 + w]; }
+            e_tot += ee;
+            l_tot += ll;
+          }
+          named_bar(3, EPI_THREADS);
+          if (GRAD && t512 < 2 * Kb) {
+            float g = 0.f;
+            for (int w = 0; w < 16; ++w) g += s.red[w * 20 + t512];
+            s.gacc[t512] += g;
+          }
+        }  // windows
+
+        named_bar(3, EPI_THREADS);
+        if (t512 == 0) {
+          const float E = e_tot / float(M);
+          if (p.energy_trace) p.energy_trace[size_t(step) * p.N + n] = E;
+          if (step == p.steps - 1) {
+            if (p.energy_last) p.energy_last[n] = E;
+            if (p.length_out) p.length_out[n] = l_tot / float(M);
+          }
+        }
+        if (GRAD && t512 < 2 * Kb) {
+          const int k = t512 >> 1, d = t512 & 1;
+          const float tend = p.t[T - 1];
+          float P[MAX_KB];
+          design_row(tend, n_poly, Kb, s.basis, P);
+          const float2 ze = spline_point(tend, n_poly, s.coef, pa, pb);
+          const float err = d == 0 ? ze.x - pb.x : ze.y - pb.y;
+          const float g = s.gacc[t512] + (2.0f * p.penalty_w) * err * P[k];
+          AdamScalars sc = adam_scalars(p.step0 + step + 1, p.lr, p.beta1, p.beta2);
+          float om = s.om[t512], mm = s.om[2 * MAX_KB + t512], vv = s.om[4 * MAX_KB + t512];
+          adam_update(om, mm, vv, g, sc, p.one_minus_b1, p.beta2f, p.one_minus_b2, p.eps);
+          s.om[t512] = om;
+          s.om[2 * MAX_KB + t512] = mm;
+          s.om[4 * MAX_KB + t512] = vv;
+        }
+        named_bar(3, EPI_THREADS);
+      }  // steps
+
+      if (GRAD && t512 < 2 * Kb) {
+        p.omega[size_t(n) * 2 * Kb + t512] = s.om[t512];
+        p.adam_m[size_t(n) * 2 * Kb + t512] = s.om[2 * MAX_KB + t512];
+        p.adam_v[size_t(n) * 2 * Kb + t512] = s.om[4 * MAX_KB + t512];
+        __threadfence();
+      }
+      named_bar(3, EPI_THREADS);
+      if (t512 == 0) {
+        const unsigned int v = unsigned(chunk) + 1u;
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&queue[64 + n]), "r"(v) : "memory");
+      }
+    }  // work units
+    // tell the control warps that there is no more work
+    if (t512 == 0) {
+      s.ctl[wcount & 1].nitems = -1;
+      __threadfence_block();
+      mbar_arrive(win_ready);
+    }
+    cp_async_wait_all();
+#ifdef VLG_TC_STATS
+    if (tg == 0 && blockIdx.x < 1024) g_tc_stats[blockIdx.x * 8 + 4 + chain_id * 2] = w_acc;
+#endif
+    (void)w_acc;
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
+static int tc_grid(int N) {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) sms = v;
+  } else {
+    (void)cudaGetLastError();
+  }
+  return N < sms ? N : sms;
+}
+
+// Window length: as few 128-row items per curve as possible.  A decoder is drawn by a point with
+// probability p = 1 - (1 - 1/K)^(2M); its row count n in a window of W points is ~Binomial(W, p) and it
+// costs ceil(n/128) items.  Evaluate the expected item count for every admissible number of windows.
+static int tc_window_points(int T, int K, int M) {
+  const double p = 1.0 - pow(1.0 - 1.0 / K, 2.0 * M);
+  const int segs = T - 1;
+  if (const char* env = getenv("VLG_TC_WINDOW")) {  // tuning override: number of windows per curve
+    const int nwin = atoi(env);
+    if (nwin >= 1) {
+      const int w = (segs + nwin - 1) / nwin + 1;
+      if (w >= 2 && w <= TC_MAX_W && tc_stages(w, K, M) >= 2) return w;
+    }
+  }
+  int best_w = 0;
+  double best = 1e300;
+  for (int nwin = 1; nwin <= segs; ++nwin) {
+    const int w = (segs + nwin - 1) / nwin + 1;  // points per window
+    if (w > TC_MAX_W) continue;
+    const int nst = tc_stages(w, K, M);
+    if (nst >= 2) {
+      const double mean = w * p, sd = sqrt(w * p * (1.0 - p)) + 1e-9;
+      double items = 0.0;
+      for (int q = 0; q * 128 < w; ++q) items += 0.5 * erfc((q * 128 + 0.5 - mean) / (sd * 1.4142135623730951));  // P(n > 128 q)
+      double cost = nwin * (K * items + 0.35);  // + per-window fixed cost in item units
+      if (nst == 2) cost *= 1.04;               // a two-stage weight ring cannot hold a whole GEMM's weights
+      if (cost < best) { best = cost; best_w = w; }
+    }
+    if (w <= 128) break;
+  }
+  return best_w;  // 0: does not fit
+}
+
+// per CTA: layer-2 ReLU mask bits [K+16 items][128 rows][4 words] + right-end outputs x2 [M][W][52] fp32
+size_t tc_workspace_bytes(int N, int T, int K, int M) {
+  if (M > TC_MAX_M || K > TC_MAX_K) return 0;
+  const int W = tc_window_points(T, K, M);
+  return tc_queue_words(N) * 4 + size_t(tc_grid(N)) * (size_t(K + 16) * 2048 + size_t(M) * W * XD_STRIDE * 4);
+}
+
+#ifdef VLG_TC_STATS
+extern "C" int vlg_debug_tc_stats(long long* host_out, int n) {
+  return cudaMemcpyFromSymbol(host_out, g_tc_stats, size_t(n) * 8 * sizeof(long long)) == cudaSuccess ? 0 : -3;
+}
+#endif
+
+cudaError_t launch_tc(const StepParams& p, bool grad, cudaStream_t stream) {
+  if (p.precision != 1 && p.precision != 3) return cudaErrorNotSupported;  // 3xTF32 not built
+  const bool f16 = p.precision == 3;
+  if (p.M > TC_MAX_M || p.K > TC_MAX_K) return cudaErrorNotSupported;
+  const int W = tc_window_points(p.T, p.K, p.M);
+  if (W < 2) return cudaErrorNotSupported;
+  const int nst = tc_stages(W, p.K, p.M);
+  if (nst < 2) return cudaErrorNotSupported;
+  if (p.workspace == nullptr || p.workspace_bytes < tc_workspace_bytes(p.N, p.T, p.K, p.M)) return cudaErrorInvalidValue;
+  const size_t smem = tc_smem_fixed_bytes(W, p.K, p.M) + size_t(2) * nst * STAGE_BYTES;
+  const int grid = tc_grid(p.N);
+  StepParams q = p;
+  // chunks of a curve per launch: at least 4, and enough work units (~48 per CTA) that the last wave's
+  // tail -- at most one unit -- stays a small fraction of the launch
+  int nchunks = (48 * grid + p.N - 1) / p.N;
+  if (nchunks < 4) nchunks = 4;
+  if (nchunks > q.steps) nchunks = q.steps;
+  q.unit_steps = (q.steps + nchunks - 1) / nchunks;
+  cudaError_t e = cudaMemsetAsync(p.workspace, 0, tc_queue_words(p.N) * 4, stream);
+  if (e != cudaSuccess) return e;
+  auto launch = [&](auto kernel) -> cudaError_t {
+    cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (err != cudaSuccess) return err;
+    kernel<<<grid, TC_THREADS, smem, stream>>>(q, nst, W);
+    return cudaGetLastError();
+  };
+  if (grad) return f16 ? launch(tc_curve_kernel<true, true>) : launch(tc_curve_kernel<true, false>);
+  return f16 ? launch(tc_curve_kernel<false, true>) : launch(tc_curve_kernel<false, false>);
+}
+
+}  // namespace vlg
