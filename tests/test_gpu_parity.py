@@ -378,14 +378,15 @@ def test_config5_shape_k64_npoly8_t256(vlg):
     r = O.optimize_steps(g["a"].astype(np.float64), g["b"].astype(np.float64), g["omega_init"].astype(np.float64),
                          g["basis"].astype(np.float64), Hh.tgrid(T, np.float64), n_poly, Hh.decoder_list(W, K, np.float64), draws, S)
     out = {}
-    for prec in ("fp32", "tf32"):
+    for prec in ("fp32", "tf32", "f16"):
         model = make_model(vlg, g)
         _, trace = vlg.optimize_splines(model, dec, t, S, M=M, seed=seed, curve_id0=id0, precision=prec, return_trace=True)
         out[prec] = (trace.cpu().numpy(), model.omega.cpu().numpy())
     assert np.abs(out["fp32"][0] / r["energy"] - 1).max() < 1e-5
     assert np.abs(out["fp32"][1] - r["omega"]).max() < 5e-6
-    assert np.abs(np.sqrt(out["tf32"][0] / r["energy"]) - 1).max() < 5e-3   # random-init nets: smooth, small energies
-    assert np.abs(out["tf32"][1] - r["omega"]).max() < 0.25 * S * 1e-3 + 1e-6
+    for tc in ("tf32", "f16"):
+        assert np.abs(np.sqrt(out[tc][0] / r["energy"]) - 1).max() < 5e-3   # random-init nets: smooth, small energies
+        assert np.abs(out[tc][1] - r["omega"]).max() < 0.25 * S * 1e-3 + 1e-6
 
 
 @pytest.mark.parametrize("prec,tol", [("fp32", 1e-3), ("tf32", 1e-3), ("f16", 1e-3)])
