@@ -2,7 +2,7 @@
 """Benchmark of the geodesic curve-energy hot path (BASELINE.json metric: spline-steps/sec,
 8778-pair 10-decoder eVAE energy optimisation).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--precision f16|tf32|fp32]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--precision f16|f16x3|tf32|fp32]
 
 A "step" is one Adam step of EVERY curve of the workload (= n_curves spline-steps): spline
 evaluation, all-decoder forward + input-gradient backward, MC pair energy, Adam -- one pass of
@@ -42,6 +42,7 @@ METRIC = "spline-steps/sec, 8778-pair 10-decoder eVAE energy opt"
 # arithmetic of the two 128-wide decoder layers (layer 1, the energy, the spline and Adam are fp32 everywhere)
 PRECISION_NOTE = {
     "f16": "f16: tcgen05 kind::f16, fp16 operands (11-bit significand, as TF32), fp32 accumulate; <=1e-3 rel. on lengths",
+    "f16x3": "f16x3: tcgen05 kind::f16, hi+lo fp16 operands, 3 MMAs per product, fp32 accumulate; fp32-grade (2e-6 rel. per-step energy)",
     "tf32": "tf32: tcgen05 kind::tf32, fp32 accumulate; <=1e-3 rel. on lengths",
     "fp32": "fp32: CUDA-core FFMA; <=1e-4 rel. per-step energy",
 }
@@ -316,7 +317,7 @@ def run_gpu_arm(args):
             "metric": METRIC, "value": value, "unit": "spline-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None,
-            "dtype": {"f16": "f16", "tf32": "tf32", "fp32": "f32"}[args.precision], "data": "synthetic",
+            "dtype": {"f16": "f16", "f16x3": "f16x3", "tf32": "tf32", "fp32": "f32"}[args.precision], "data": "synthetic",
             "config": dict(workload_config(weights, world, "gpu"), precision=PRECISION_NOTE[args.precision],
                            steps_per_launch=chunk),
             "clocks": clocks,
@@ -326,8 +327,8 @@ def run_gpu_arm(args):
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": {"f16": "tc_curve_kernel<true, true>", "tf32": "tc_curve_kernel<true, false>",
-                                    "fp32": "simt_curve_kernel<true>"}[args.precision],
+                         "kernel": {"f16": "tc_curve_kernel<true, FMT_F16>", "f16x3": "tc_curve_kernel<true, FMT_F16X3>",
+                                    "tf32": "tc_curve_kernel<true, FMT_TF32>", "fp32": "simt_curve_kernel<true>"}[args.precision],
                          "flop_per_spline_step": T_POINTS * K_DEC * FLOP_PER_POINT_DECODER,
                          "kernel_ms_per_step": kernel_ms / args.steps},
         }
@@ -347,7 +348,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="vlg", choices=["vlg", "reference"])
-    ap.add_argument("--precision", default="f16", choices=["f16", "tf32", "fp32"])
+    ap.add_argument("--precision", default="f16", choices=["f16", "f16x3", "tf32", "fp32"])
     ap.add_argument("--chunk", type=int, default=50, help="Adam steps per kernel launch")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

@@ -100,7 +100,7 @@ if __name__ == "__main__":
     parser.add_argument("--steps", type=int, default=100)
     parser.add_argument("--batch-size", type=int, default=200, help="accepted for compatibility; ignored")
     parser.add_argument("--mc-samples", type=int, default=2)
-    parser.add_argument("--precision", type=str, default="tf32", choices=["f16", "tf32", "fp32"],
+    parser.add_argument("--precision", type=str, default="tf32", choices=["f16", "f16x3", "tf32", "fp32"],
                         help="tf32 / f16: tcgen05 tensor-core kernel with TF32 or fp16 operands (<=1e-3 on lengths; f16 is ~1.25x faster, operands must stay below 65504); fp32: CUDA-core kernel")
     parser.add_argument("--seed", type=int, default=0, help="seed of the decoder-pair draws")
     args = parser.parse_args()

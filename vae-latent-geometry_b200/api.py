@@ -134,7 +134,7 @@ def _resolve_precision(precision: str, decoders, M: int) -> int:
     (M > 2 MC samples or more than 64 decoders) and for a single active decoder, where TF32 cannot
     resolve the tiny adjacent-point differences (SURVEY hard part 1).  Still a GPU kernel -- there is no
     CPU path."""
-    if precision in ("tf32", "f16") and (M > TC_MAX_M or len(decoders) > TC_MAX_K):
+    if precision in ("tf32", "f16", "f16x3", "tf32x3") and (M > TC_MAX_M or len(decoders) > TC_MAX_K):
         import warnings
         warnings.warn(f"tensor-core kernel supports M <= {TC_MAX_M}, K <= {TC_MAX_K}; using the fp32 kernel")
         precision = "fp32"

@@ -33,6 +33,7 @@ constexpr int MAX_K = 255;      // decoder index travels as uint8; 255 = "none"
 //   the same four matrices as fp16 images (round-to-nearest) for kind::f16,
 //   img16[k/8][n][k%8] (16-bit elements: a 16-byte core-matrix row holds 8 k; same SBO / LBO):
 //   W2_H, W3_H, W3T_H, W2T_H  (offsets below are in floats; an image of N x K halves takes N*K/2)
+//   and their fp16 residuals W2_HL, W3_HL, W3T_HL, W2T_HL = fp16(w - fp16(w))
 // ---------------------------------------------------------------------------------------
 struct PackedHeader {
   uint32_t magic;    // 'VLG1'
@@ -60,7 +61,12 @@ constexpr int OFF_W2_H = OFF_W2T_UMMA + H * H;
 constexpr int OFF_W3_H = OFF_W2_H + H * H / 2;
 constexpr int OFF_W3T_H = OFF_W3_H + XP * H / 2;
 constexpr int OFF_W2T_H = OFF_W3T_H + XP * H / 2;
-constexpr int DEC_FLOATS = OFF_W2T_H + H * H / 2;
+// residual images fp16(w - fp16(w)) in the same layout, for the 3-term split mode (fp32-grade on the tensor pipe)
+constexpr int OFF_W2_HL = OFF_W2T_H + H * H / 2;
+constexpr int OFF_W3_HL = OFF_W2_HL + H * H / 2;
+constexpr int OFF_W3T_HL = OFF_W3_HL + XP * H / 2;
+constexpr int OFF_W2T_HL = OFF_W3T_HL + XP * H / 2;
+constexpr int DEC_FLOATS = OFF_W2T_HL + H * H / 2;
 static_assert(DEC_FLOATS % 64 == 0 && OFF_W2_UMMA % 4 == 0, "images must stay 16-byte aligned");
 
 __host__ __device__ inline const float* dec_ptr(const void* packed, int k) {

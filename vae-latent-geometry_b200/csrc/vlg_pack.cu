@@ -51,8 +51,11 @@ __global__ void pack_kernel(const float* __restrict__ W1, const float* __restric
     d[OFF_W2_UMMA + u] = hi;
     d[OFF_W2T_UMMA + ut] = hi;
     const __half wh = __float2half_rn(w);
+    const __half wl = __float2half_rn(w - __half2float(wh));
     reinterpret_cast<__half*>(d + OFF_W2_H)[((in >> 3) * H + o) * 8 + (in & 7)] = wh;
     reinterpret_cast<__half*>(d + OFF_W2T_H)[((o >> 3) * H + in) * 8 + (o & 7)] = wh;
+    reinterpret_cast<__half*>(d + OFF_W2_HL)[((in >> 3) * H + o) * 8 + (in & 7)] = wl;
+    reinterpret_cast<__half*>(d + OFF_W2T_HL)[((o >> 3) * H + in) * 8 + (o & 7)] = wl;
   }
   for (int i = threadIdx.x; i < XP * H; i += blockDim.x) {
     const int o = i / H, in = i % H;  // W3[o][in], zero rows o >= X
@@ -65,8 +68,11 @@ __global__ void pack_kernel(const float* __restrict__ W1, const float* __restric
     d[OFF_W3_UMMA + u] = hi;
     d[OFF_W3T_UMMA + ut] = hi;
     const __half wh = __float2half_rn(w);
+    const __half wl = __float2half_rn(w - __half2float(wh));
     reinterpret_cast<__half*>(d + OFF_W3_H)[((in >> 3) * XP + o) * 8 + (in & 7)] = wh;   // N = 64, K = 128
     reinterpret_cast<__half*>(d + OFF_W3T_H)[((o >> 3) * H + in) * 8 + (o & 7)] = wh;    // N = 128, K = 64
+    reinterpret_cast<__half*>(d + OFF_W3_HL)[((in >> 3) * XP + o) * 8 + (in & 7)] = wl;
+    reinterpret_cast<__half*>(d + OFF_W3T_HL)[((o >> 3) * H + in) * 8 + (o & 7)] = wl;
   }
 }
 

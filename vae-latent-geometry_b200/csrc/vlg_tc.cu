@@ -76,28 +76,44 @@ struct OpInfo {
   int nk;        // MMAs per stage (8 TMEM columns of A each: 8 tf32 or 16 fp16 contraction indices)
   int a_col;     // chain-relative TMEM column of A
   int d_col;     // chain-relative TMEM column of D
+  int img_lo;    // 3-term mode: float offset of the residual image
 };
+// operand formats of the tensor-core kernel
+constexpr int FMT_TF32 = 0, FMT_F16 = 1, FMT_F16X3 = 2;
 // kind::tf32: activations are fp32 words with TF32-rounded bits, one per TMEM column; an accumulator is
 // overwritten in place by the next layer's operand (X = columns 0..127 of the chain, Y = 128..255).
 // kind::f16 : activations are fp16 pairs, two per column, so an operand takes half the columns of the
 // accumulator it was computed from and cannot be written in place (another thread's accumulator
 // columns would be hit): operands always go to X[0:64], accumulators to Y or X[64:128].
-template <bool F16>
+// 3-term mode (FMT_F16X3): every operand is the sum of two fp16 numbers, hi = fp16(v) and lo = fp16(v - hi)
+// (~21 significant bits); a product is evaluated as hi*hi + lo*hi + hi*lo in the fp32 accumulator -- three
+// times the MMAs of FMT_F16, fp32-grade results.  The residual operand sits 64 columns above the main one
+// (X[64:128]), so every accumulator -- D3 included -- goes to Y.
+template <int FMT>
 __device__ __forceinline__ OpInfo op_info(int op) {
-  if (F16) {
+  if (FMT != FMT_TF32) {
+    const int d3 = FMT == FMT_F16X3 ? 128 : 64;
     switch (op) {
-      case 0: return {OFF_W2_H, 2, 128, 4, 0, 128};     // F2: D2(Y) = A1(X[0:64]) * W2^T
-      case 1: return {OFF_W3_H, 1, 64, 8, 0, 64};       // F3: D3(X[64:128]) = A2(X[0:64]) * W3^T
-      case 2: return {OFF_W3T_H, 1, 128, 4, 0, 128};    // B3: D4(Y) = G(X[0:32]) * W3
-      default: return {OFF_W2T_H, 2, 128, 4, 0, 128};   // B2: D5(Y) = A4(X[0:64]) * W2
+      case 0: return {OFF_W2_H, 2, 128, 4, 0, 128, OFF_W2_HL};     // F2: D2(Y) = A1(X[0:64]) * W2^T
+      case 1: return {OFF_W3_H, 1, 64, 8, 0, d3, OFF_W3_HL};       // F3: D3(X[64:128] | Y[0:64]) = A2(X[0:64]) * W3^T
+      case 2: return {OFF_W3T_H, 1, 128, 4, 0, 128, OFF_W3T_HL};   // B3: D4(Y) = G(X[0:32]) * W3
+      default: return {OFF_W2T_H, 2, 128, 4, 0, 128, OFF_W2T_HL};  // B2: D5(Y) = A4(X[0:64]) * W2
     }
   }
   switch (op) {
-    case 0: return {OFF_W2_UMMA, 4, 128, 4, 0, 128};    // F2: D2(Y) = A1(X) * W2^T
-    case 1: return {OFF_W3_UMMA, 2, 64, 8, 128, 0};     // F3: D3(X[0:64]) = A2(Y) * W3^T
-    case 2: return {OFF_W3T_UMMA, 2, 128, 4, 0, 128};   // B3: D4(Y) = G(X[0:64]) * W3
-    default: return {OFF_W2T_UMMA, 4, 128, 4, 128, 0};  // B2: D5(X) = A4(Y) * W2
+    case 0: return {OFF_W2_UMMA, 4, 128, 4, 0, 128, 0};    // F2: D2(Y) = A1(X) * W2^T
+    case 1: return {OFF_W3_UMMA, 2, 64, 8, 128, 0, 0};     // F3: D3(X[0:64]) = A2(Y) * W3^T
+    case 2: return {OFF_W3T_UMMA, 2, 128, 4, 0, 128, 0};   // B3: D4(Y) = G(X[0:64]) * W3
+    default: return {OFF_W2T_UMMA, 4, 128, 4, 128, 0, 0};  // B2: D5(X) = A4(Y) * W2
   }
+}
+// hi / lo fp16 pairs of two fp32 values
+__device__ __forceinline__ void pack_hilo_h2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 back = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - back.x, b - back.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 // two fp32 -> one fp16x2 word (round-to-nearest; lo half = first argument), optionally through relu
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
@@ -240,8 +256,10 @@ static int tc_stages(int W, int K, int M) {
   return int(nst);
 }
 
-template <bool GRAD, bool F16>
+template <bool GRAD, int FMT>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, int nst, int W) {
+  constexpr bool F16 = FMT != FMT_TF32;   // fp16 operands (one or two terms)
+  constexpr bool X3 = FMT == FMT_F16X3;   // 3-term split
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int M = p.M, K = p.K, T = p.T, n_poly = p.n_poly, Kb = p.Kb;
@@ -299,12 +317,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
           for (int i = c; i < nit; i += 2) {
             const int k = ctl->item[i] & 0xFF;
             for (int o = 0; o < 2; ++o) {
-              const OpInfo oi = op_info<F16>(phase * 2 + o);
+              const OpInfo oi = op_info<FMT>(phase * 2 + o);
               const char* src = reinterpret_cast<const char*>(dec_ptr(p.packed, k) + oi.img_off);
-              for (int st = 0; st < oi.nstages; ++st) {
+              const char* src_lo = reinterpret_cast<const char*>(dec_ptr(p.packed, k) + oi.img_lo);
+              // 3-term mode: the stages of the main image, then the stages of the residual image
+              for (int st = 0; st < (X3 ? 2 : 1) * oi.nstages; ++st) {
+                const char* from = st < oi.nstages ? src + size_t(st) * STAGE_BYTES : src_lo + size_t(st - oi.nstages) * STAGE_BYTES;
                 mbar_wait(&emptyc[slot], ph ^ 1);
                 mbar_expect_tx(&fullc[slot], STAGE_BYTES);
-                bulk_g2s(ringc + slot * STAGE_BYTES, src + size_t(st) * STAGE_BYTES, STAGE_BYTES, &fullc[slot]);
+                bulk_g2s(ringc + slot * STAGE_BYTES, from, STAGE_BYTES, &fullc[slot]);
                 if (++slot == nst) { slot = 0; ph ^= 1; }
               }
             }
@@ -351,28 +372,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
           tc_fence_after();
           // op order inside a window: F2 F3 per item, then B3 B2 per item
           const int optype = (opi[c] < 2 * nitc[c]) ? (opi[c] & 1) : 2 + ((opi[c] - 2 * nitc[c]) & 1);
-          const OpInfo oi = op_info<F16>(optype);
+          const OpInfo oi = op_info<FMT>(optype);
           const uint32_t idesc = F16 ? umma_idesc_f16(oi.n) : umma_idesc_tf32(oi.n, 0);
           const uint32_t chain = tmem + uint32_t(c) * 256u;
           uint64_t* fullc = full + c * MAX_STAGES;
           uint64_t* emptyc = empty + c * MAX_STAGES;
           const unsigned char* ringc = s.ring + c * nst * STAGE_BYTES;
-          for (int st = 0; st < oi.nstages; ++st) {
+          for (int st = 0; st < (X3 ? 2 : 1) * oi.nstages; ++st) {
             if (!mbar_test(&fullc[slot[c]], ph[c])) { STAT_T0(); mbar_wait(&fullc[slot[c]], ph[c]); STAT_ADD(w_full); }
             tc_fence_after();
             const uint32_t sbase = smem_u32(ringc + slot[c] * STAGE_BYTES);
             const int nk = oi.nk;
+            const bool w_lo = X3 && st >= oi.nstages;          // this stage holds residual weights
+            const int kst = w_lo ? st - oi.nstages : st;       // which slice of the contraction
             {
               STAT_T0();
-              for (int ks = 0; ks < nk; ++ks) {
-                const uint64_t desc =
-                    umma_smem_desc(sbase + uint32_t(ks) * 2u * uint32_t(oi.n) * 16u, uint32_t(oi.n) * 16u, 128u);
-                const uint32_t a_addr = chain + oi.a_col + uint32_t((st * nk + ks) * 8);
-                if (F16)
-                  umma_f16_ts_elect(chain + oi.d_col, a_addr, desc, idesc, (st | ks) ? 1u : 0u, leader);
-                else
-                  umma_tf32_ts_elect(chain + oi.d_col, a_addr, desc, idesc, (st | ks) ? 1u : 0u, leader);
-              }
+              // main weights: main operand (and, 3-term mode, the residual operand 64 columns up);
+              // residual weights: main operand only
+              for (int term = 0; term < ((X3 && !w_lo) ? 2 : 1); ++term)
+                for (int ks = 0; ks < nk; ++ks) {
+                  const uint64_t desc =
+                      umma_smem_desc(sbase + uint32_t(ks) * 2u * uint32_t(oi.n) * 16u, uint32_t(oi.n) * 16u, 128u);
+                  const uint32_t a_addr = chain + oi.a_col + uint32_t(term * 64) + uint32_t((kst * nk + ks) * 8);
+                  const uint32_t accum = (st | ks | term) ? 1u : 0u;
+                  if (F16)
+                    umma_f16_ts_elect(chain + oi.d_col, a_addr, desc, idesc, accum, leader);
+                  else
+                    umma_tf32_ts_elect(chain + oi.d_col, a_addr, desc, idesc, accum, leader);
+                }
               umma_commit_elect(&emptyc[slot[c]], leader);
               STAT_ADD(w_issue);
             }
@@ -555,21 +582,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
             // layer 1 (CUDA cores, fp32) -> A1 in X[col0 : col0+64]  (fp16: pairs in X[32 half : +32])
             if (F16) {
               if (wact) {
-                uint32_t v[32];
 #pragma unroll
-                for (int j = 0; j < 64; j += 4) {
-                  const int c = col0 + j;
-                  const float4 wx = *reinterpret_cast<const float4*>(sw + OFF_W1X + c);
-                  const float4 wy = *reinterpret_cast<const float4*>(sw + OFF_W1Y + c);
-                  const float4 bb = *reinterpret_cast<const float4*>(sw + OFF_B1 + c);
-                  const float2 h0 = __ffma2_rn(make_float2(wy.x, wy.y), zy2,
-                                               __ffma2_rn(make_float2(wx.x, wx.y), zx2, make_float2(bb.x, bb.y)));
-                  const float2 h1 = __ffma2_rn(make_float2(wy.z, wy.w), zy2,
-                                               __ffma2_rn(make_float2(wx.z, wx.w), zx2, make_float2(bb.z, bb.w)));
-                  v[j >> 1] = pack_relu_h2(h0.x, h0.y);
-                  v[(j >> 1) + 1] = pack_relu_h2(h1.x, h1.y);
+                for (int hh = 0; hh < 2; ++hh) {   // 32 hidden units = 16 packed columns per pass
+                  uint32_t v[16], vl[16];
+#pragma unroll
+                  for (int j = 0; j < 32; j += 4) {
+                    const int c = col0 + 32 * hh + j;
+                    const float4 wx = *reinterpret_cast<const float4*>(sw + OFF_W1X + c);
+                    const float4 wy = *reinterpret_cast<const float4*>(sw + OFF_W1Y + c);
+                    const float4 bb = *reinterpret_cast<const float4*>(sw + OFF_B1 + c);
+                    const float2 h0 = __ffma2_rn(make_float2(wy.x, wy.y), zy2,
+                                                 __ffma2_rn(make_float2(wx.x, wx.y), zx2, make_float2(bb.x, bb.y)));
+                    const float2 h1 = __ffma2_rn(make_float2(wy.z, wy.w), zy2,
+                                                 __ffma2_rn(make_float2(wx.z, wx.w), zx2, make_float2(bb.z, bb.w)));
+                    if (X3) {
+                      pack_hilo_h2(fmaxf(h0.x, 0.f), fmaxf(h0.y, 0.f), v[j >> 1], vl[j >> 1]);
+                      pack_hilo_h2(fmaxf(h1.x, 0.f), fmaxf(h1.y, 0.f), v[(j >> 1) + 1], vl[(j >> 1) + 1]);
+                    } else {
+                      v[j >> 1] = pack_relu_h2(h0.x, h0.y);
+                      v[(j >> 1) + 1] = pack_relu_h2(h1.x, h1.y);
+                    }
+                  }
+                  tmem_st16(colX + half * 32 + 16 * hh, v);
+                  if (X3) tmem_st16(colX + 64 + half * 32 + 16 * hh, vl);
                 }
-                tmem_st32(colX + half * 32, v);
               }
             } else if (wact) {
 #pragma unroll
@@ -606,6 +642,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
 #pragma unroll
               for (int hh = 0; hh < 2; ++hh) {
                 uint32_t v[32];
+                uint32_t vlo[X3 ? 16 : 1];
                 tmem_ld32_sync(colY + col0 + 32 * hh, v);
                 uint32_t bb = 0;
 #pragma unroll
@@ -617,7 +654,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                   if (p0.y > 0.f) bb |= 2u << j;
                   if (p1.x > 0.f) bb |= 4u << j;
                   if (p1.y > 0.f) bb |= 8u << j;
-                  if (F16) {
+                  if (X3) {
+                    uint32_t a0, a1;
+                    pack_hilo_h2(fmaxf(p0.x, 0.f), fmaxf(p0.y, 0.f), a0, vlo[j >> 1]);
+                    pack_hilo_h2(fmaxf(p1.x, 0.f), fmaxf(p1.y, 0.f), a1, vlo[(j >> 1) + 1]);
+                    v[j >> 1] = a0;
+                    v[(j >> 1) + 1] = a1;
+                  } else if (F16) {
                     // pairs go to v[0:16] (slots j/2, j/2+1 <= j were consumed already)
                     const uint32_t a0 = pack_relu_h2(p0.x, p0.y), a1 = pack_relu_h2(p1.x, p1.y);
                     v[j >> 1] = a0;
@@ -631,6 +674,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                   tmem_st16(colX + half * 32 + 16 * hh, reinterpret_cast<uint32_t(&)[16]>(v));
                 else
                   tmem_st32(colY + col0 + 32 * hh, v);
+                if (X3) tmem_st16(colX + 64 + half * 32 + 16 * hh, reinterpret_cast<uint32_t(&)[16]>(vlo));
               }
               if (GRAD && active) *reinterpret_cast<uint2*>(maskws + (it * 128 + row) * 4 + half * 2) = make_uint2(bits[0], bits[1]);
             }
@@ -643,7 +687,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
             tc_fence_after();
             if (wact) {
               uint32_t xv[32];
-              tmem_ld32_sync(colX + (F16 ? 64 : 0) + xc0, xv);
+              tmem_ld32_sync((X3 ? colY : colX + (F16 ? 64 : 0)) + xc0, xv);
               float x[32];
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
@@ -790,10 +834,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                   }
                 }
                 if (F16) {
-                  uint32_t v[16];
+                  uint32_t v[16], vl[X3 ? 16 : 1];
 #pragma unroll
-                  for (int j = 0; j < 16; ++j) v[j] = pack_h2((coefm * F16_GRAD_SCALE) * g[2 * j], (coefm * F16_GRAD_SCALE) * g[2 * j + 1]);
+                  for (int j = 0; j < 16; ++j) {
+                    const float g0 = (coefm * F16_GRAD_SCALE) * g[2 * j], g1 = (coefm * F16_GRAD_SCALE) * g[2 * j + 1];
+                    if (X3)
+                      pack_hilo_h2(g0, g1, v[j], vl[j]);
+                    else
+                      v[j] = pack_h2(g0, g1);
+                  }
                   tmem_st16(colX + half * 16, v);
+                  if (X3) tmem_st16(colX + 64 + half * 16, reinterpret_cast<uint32_t(&)[16]>(vl));
                 } else {
                   uint32_t v[32];
 #pragma unroll
@@ -815,13 +866,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                   tmem_ld32_sync(colY + col0 + 32 * hh, v);
                   const uint32_t mb = hh ? bits.y : bits.x;
                   if (F16) {
+                    uint32_t vl[X3 ? 16 : 1];
 #pragma unroll
                     for (int j = 0; j < 32; j += 2) {
                       const float a0 = ((mb >> j) & 1u) ? __uint_as_float(v[j]) : 0.f;
                       const float a1 = ((mb >> (j + 1)) & 1u) ? __uint_as_float(v[j + 1]) : 0.f;
-                      v[j >> 1] = pack_h2(a0, a1);   // j/2 <= j: slot already consumed
+                      if (X3)
+                        pack_hilo_h2(a0, a1, v[j >> 1], vl[j >> 1]);
+                      else
+                        v[j >> 1] = pack_h2(a0, a1);   // j/2 <= j: slot already consumed
                     }
                     tmem_st16(colX + half * 32 + 16 * hh, reinterpret_cast<uint32_t(&)[16]>(v));
+                    if (X3) tmem_st16(colX + 64 + half * 32 + 16 * hh, reinterpret_cast<uint32_t(&)[16]>(vl));
                   } else {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = ((mb >> j) & 1u) ? tf32_round_bits(v[j]) : 0u;
@@ -1018,8 +1074,8 @@ extern "C" int vlg_debug_tc_stats(long long* host_out, int n) {
 #endif
 
 cudaError_t launch_tc(const StepParams& p, bool grad, cudaStream_t stream) {
-  if (p.precision != 1 && p.precision != 3) return cudaErrorNotSupported;  // 3xTF32 not built
-  const bool f16 = p.precision == 3;
+  if (p.precision < 1 || p.precision > 3) return cudaErrorNotSupported;
+  const int fmt = p.precision == 1 ? FMT_TF32 : p.precision == 3 ? FMT_F16 : FMT_F16X3;
   if (p.M > TC_MAX_M || p.K > TC_MAX_K) return cudaErrorNotSupported;
   const int W = tc_window_points(p.T, p.K, p.M);
   if (W < 2) return cudaErrorNotSupported;
@@ -1043,8 +1099,11 @@ cudaError_t launch_tc(const StepParams& p, bool grad, cudaStream_t stream) {
     kernel<<<grid, TC_THREADS, smem, stream>>>(q, nst, W);
     return cudaGetLastError();
   };
-  if (grad) return f16 ? launch(tc_curve_kernel<true, true>) : launch(tc_curve_kernel<true, false>);
-  return f16 ? launch(tc_curve_kernel<false, true>) : launch(tc_curve_kernel<false, false>);
+  if (grad)
+    return fmt == FMT_TF32 ? launch(tc_curve_kernel<true, FMT_TF32>)
+           : fmt == FMT_F16 ? launch(tc_curve_kernel<true, FMT_F16>) : launch(tc_curve_kernel<true, FMT_F16X3>);
+  return fmt == FMT_TF32 ? launch(tc_curve_kernel<false, FMT_TF32>)
+         : fmt == FMT_F16 ? launch(tc_curve_kernel<false, FMT_F16>) : launch(tc_curve_kernel<false, FMT_F16X3>);
 }
 
 }  // namespace vlg
