@@ -147,8 +147,14 @@ __global__ void __launch_bounds__(384) mma_rate_kernel(int N, int iters, int lbo
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem = tmem_base_s;
-  if (tid == 0) {
-    const uint32_t idesc = tc::umma_idesc_tf32(N, 0);
+  if (warp == 0) {
+    // The whole warp runs the issue loop convergently, one elected lane's instructions take effect (as in the
+    // product kernel: a divergent `if (tid == 0)` loop is itself the bottleneck at ~100+ cycles per MMA).
+    // mode bit8 (256): M = 64 instead of 128; bit9 (512): kind::f16 (K = 16) instead of kind::tf32
+    const uint32_t leader = tc::elect_one();
+    uint32_t idesc = (mode & 512) ? tc::umma_idesc_f16(N) : tc::umma_idesc_tf32(N, 0);
+    if (mode & 256) idesc = (idesc & ~(0x1Fu << 24)) | (uint32_t(64 >> 4) << 24);
+    const bool f16k = (mode & 512) != 0;
     const uint32_t sb = tc::smem_u32(smem);
     const long long t0 = clock64();
     // mode bits 5..7: commit to a scratch mbarrier every 4 MMAs (32), switch the accumulator between two
@@ -157,21 +163,25 @@ __global__ void __launch_bounds__(384) mma_rate_kernel(int N, int iters, int lbo
       const int ks = i & 7;
       const uint64_t desc = tc::umma_smem_desc(sb + uint32_t(ks) * 2u * uint32_t(lbo), uint32_t(lbo), uint32_t(sbo));
       const uint32_t dcol = ((mode & 64) && ((i >> 3) & 1)) ? 256u : 128u;
-      tc::umma_tf32_ts(tmem + dcol, tmem + uint32_t(ks) * 8u, desc, idesc, ((mode & 128) && (i & 15) == 0) ? 0u : 1u);
-      if ((mode & 32) && (i & 3) == 3) tc::umma_commit(&bar_scratch);
+      const uint32_t accum = ((mode & 128) && (i & 15) == 0) ? 0u : 1u;
+      if (f16k)
+        tc::umma_f16_ts_elect(tmem + dcol, tmem + uint32_t(ks) * 8u, desc, idesc, accum, leader);
+      else
+        tc::umma_tf32_ts_elect(tmem + dcol, tmem + uint32_t(ks) * 8u, desc, idesc, accum, leader);
+      if ((mode & 32) && (i & 3) == 3) tc::umma_commit_elect(&bar_scratch, leader);
     }
-    tc::umma_commit(&bar_mma);
+    tc::umma_commit_elect(&bar_mma, leader);
     tc::mbar_wait(&bar_mma, 0);
-    out[blockIdx.x] = clock64() - t0;
+    if (tid == 0) out[blockIdx.x] = clock64() - t0;
     if (iters > 0 && (mode & 16)) {
       // completion latency of one MMA + commit issued into an idle pipe
       const long long t1 = clock64();
-      tc::umma_tf32_ts(tmem + 128u, tmem, tc::umma_smem_desc(sb, uint32_t(lbo), uint32_t(sbo)), idesc, 1u);
-      tc::umma_commit(&bar_mma);
+      tc::umma_tf32_ts_elect(tmem + 128u, tmem, tc::umma_smem_desc(sb, uint32_t(lbo), uint32_t(sbo)), idesc, 1u, leader);
+      tc::umma_commit_elect(&bar_mma, leader);
       tc::mbar_wait(&bar_mma, 1);
-      out[2 * gridDim.x + blockIdx.x] = clock64() - t1;
+      if (tid == 0) out[2 * gridDim.x + blockIdx.x] = clock64() - t1;
     }
-    done = 1;
+    if (tid == 0) done = 1;
   } else if (warp >= 4) {
     // interference generators: mode bit0 = TMEM ld/st traffic (columns 384..447), bit1 = shared-memory loads
     const uint32_t lane_addr = uint32_t((warp & 3) * 32) << 16;
