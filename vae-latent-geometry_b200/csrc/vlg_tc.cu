@@ -186,7 +186,7 @@ struct TcSmem {
   uint16_t* rows;       // [K][W] points of the window that drew decoder k
   int* cnt;             // [K]
   WinCtl* ctl;          // [2] item lists, double buffered by window parity
-  float* sw;            // [chain][buf] 576 floats
+  float* sw;            // [chain][SW_SLOTS] 576 floats: W1 (planar), b1, b2, b3 of an item's decoder
   float2* zs;           // W latent points of the window
   float2* dzs;          // [chain][half][W]
   float* coef;          // 64
@@ -194,18 +194,19 @@ struct TcSmem {
   float* om;            // 56
   float* gacc;          // 20
   float* red;           // 16*20 + 32
-  uint64_t* bars;       // full[2][MAX_STAGES], empty[2][MAX_STAGES], a_ready[2], acc_ready[2], win_ready
+  uint64_t* bars;       // full[2][MAX_STAGES], empty[2][MAX_STAGES], a_ready[2], acc_ready[2], win_ready, sw_full[2][SW_SLOTS]
   uint32_t* tmem_base;  // [0] TMEM base address, [1] current work unit
 };
 
 constexpr int CTL_FLOATS = (2 * sizeof(WinCtl) + 3) / 4;
-constexpr int BAR_WORDS = 2 * (4 * MAX_STAGES + 5);
+constexpr int SW_SLOTS = 4;            // small-weight buffers per chain (see the producer)
+constexpr int BAR_WORDS = 2 * (4 * MAX_STAGES + 5 + 2 * SW_SLOTS);
 
 // Fixed-size pieces first, at compile-time offsets from the start of dynamic shared memory (their
 // addresses fold into immediates -- the epilogue code is short of registers), then the window-sized
 // arrays, then the weight rings.
-constexpr int FIX_SW = 0;                                   // 4 x 576
-constexpr int FIX_COEF = FIX_SW + 4 * 576;                  // 64
+constexpr int FIX_SW = 0;                                   // 2 chains x SW_SLOTS x 576
+constexpr int FIX_COEF = FIX_SW + 2 * SW_SLOTS * 576;       // 64
 constexpr int FIX_BASIS = FIX_COEF + 64;                    // 4 * MAX_NPOLY * MAX_KB
 constexpr int FIX_OM = FIX_BASIS + 4 * MAX_NPOLY * MAX_KB;  // 3 * 2 * MAX_KB + 2
 constexpr int FIX_GACC = FIX_OM + 3 * 2 * MAX_KB + 2;       // 2 * MAX_KB + 2
@@ -270,6 +271,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
   uint64_t* a_ready = s.bars + 4 * MAX_STAGES;
   uint64_t* acc_ready = s.bars + 4 * MAX_STAGES + 2;
   uint64_t* win_ready = s.bars + 4 * MAX_STAGES + 4;
+  uint64_t* sw_full = s.bars + 4 * MAX_STAGES + 5;   // [chain][SW_SLOTS]
   const int nwin = (T - 1 + WSEG - 1) / WSEG;
   // work queue (zeroed by the host before the launch): [0] next unit, [64 + n] chunks done of curve n
   unsigned int* queue = reinterpret_cast<unsigned int*>(p.workspace);
@@ -287,6 +289,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
     mbar_init(&acc_ready[0], 1);
     mbar_init(&acc_ready[1], 1);
     mbar_init(win_ready, 1);
+    for (int i = 0; i < 2 * SW_SLOTS; ++i) mbar_init(&sw_full[i], 1);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(s.tmem_base, 512);
@@ -308,6 +311,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
       unsigned char* ringc = s.ring + c * nst * STAGE_BYTES;
       int slot = 0;
       uint32_t ph = 0;
+      unsigned swj = 0;   // stream index of the chain's items (forward and backward items of all windows)
       for (long w = 0;; ++w) {
         mbar_wait(win_ready, uint32_t(w & 1));
         const WinCtl* ctl = &s.ctl[w & 1];
@@ -316,6 +320,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
         for (int phase = 0; phase < (GRAD ? 2 : 1); ++phase)
           for (int i = c; i < nit; i += 2) {
             const int k = ctl->item[i] & 0xFF;
+            // Small weights of this item into slot swj % SW_SLOTS.  No "slot free" barrier is needed: the
+            // producer is here only after it issued every weight stage of the previous item, the last of
+            // which went into a ring slot that an MMA of item j-1 or j-2 had released (the ring holds at
+            // most 4 stages, an item has at least 3) -- so the epilogue threads, which all arrive before
+            // an MMA is issued, are past item j-3, and slot j % 4 was last read by item j-4.
+            {
+              uint64_t* bar = &sw_full[c * SW_SLOTS + (swj % SW_SLOTS)];
+              mbar_expect_tx(bar, 576 * 4);
+              bulk_g2s(s.sw + (c * SW_SLOTS + (swj % SW_SLOTS)) * 576, dec_ptr(p.packed, k), 576 * 4, bar);
+              ++swj;
+            }
             for (int o = 0; o < 2; ++o) {
               const OpInfo oi = op_info<FMT>(phase * 2 + o);
               const char* src = reinterpret_cast<const char*>(dec_ptr(p.packed, k) + oi.img_off);
@@ -434,8 +449,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
     const int xc0 = half * 32;                  // this thread's output / G columns
     const int nq = half ? (XD_STRIDE - 32) / 4 : 8;  // float4 groups of this thread's output columns
     const int bar_id = 1 + chain_id;
-    float* swbuf = s.sw + chain_id * 2 * 576;
-    int swsel = 0;
+    float* swbuf = s.sw + chain_id * SW_SLOTS * 576;
+    unsigned swj = 0;                           // stream index of this chain's items, as in the producer
     uint32_t ph_acc = 0;
     const float coefm = 2.0f / float(M);
     long long w_acc = 0;
@@ -554,10 +569,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
           }
           named_bar(3, EPI_THREADS);
           const int nitems = ctl->nitems;
-          // small weights (W1, b1, b2, b3) of this group's first item
-          if (chain_id < nitems && tg < 144)
-            cp_async16(swbuf + swsel * 576 + tg * 4, dec_ptr(p.packed, ctl->item[chain_id] & 0xFF) + tg * 4);
-
           // =============================== forward ===============================
           for (int it = chain_id; it < nitems; it += 2) {
             const int k = ctl->item[it] & 0xFF, q0 = (ctl->item[it] >> 8) * 128;
@@ -566,17 +577,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
             // its 32 rows is in use; unused lanes compute on point 0 and store nothing
             const bool wact = q0 + (warp & 3) * 32 < s.cnt[k];
             const int pt = active ? s.rows[k * W + q0 + row] : 0;
-            // small weights of decoder k were prefetched into swbuf[swsel]; prefetch the next item's
-            cp_async_wait_all();
-            named_bar(bar_id, GROUP_THREADS);
-            const float* sw = swbuf + swsel * 576;
-            {
-              int nx = it + 2;
-              if (nx >= nitems) nx = GRAD ? chain_id : -1;
-              if (nx >= 0 && tg < 144)
-                cp_async16(swbuf + (swsel ^ 1) * 576 + tg * 4, dec_ptr(p.packed, ctl->item[nx] & 0xFF) + tg * 4);
-            }
-            swsel ^= 1;
+            // small weights of decoder k: loaded by the chain's producer (bulk copy -> mbarrier).  TF32
+            // operands overwrite accumulators in place, so the group must also be done with the previous
+            // item's D3 before layer 1 is stored; fp16 operands and accumulators never share columns.
+            mbar_wait(&sw_full[chain_id * SW_SLOTS + (swj % SW_SLOTS)], (swj / SW_SLOTS) & 1u);
+            if (!F16) named_bar(bar_id, GROUP_THREADS);
+            const float* sw = swbuf + (swj % SW_SLOTS) * 576;
+            ++swj;
             const float2 z = s.zs[pt];
             const float2 zx2 = make_float2(z.x, z.x), zy2 = make_float2(z.y, z.y);
             // layer 1 (CUDA cores, fp32) -> A1 in X[col0 : col0+64]  (fp16: pairs in X[32 half : +32])
@@ -794,15 +801,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
               const bool active = q0 + row < s.cnt[k];
               const bool wact = q0 + (warp & 3) * 32 < s.cnt[k];
               const int pt = active ? s.rows[k * W + q0 + row] : 0;
-              cp_async_wait_all();
-              named_bar(bar_id, GROUP_THREADS);
-              const float* sw = swbuf + swsel * 576;
-              {
-                const int nx = it + 2;
-                if (nx < nitems && tg < 144)
-                  cp_async16(swbuf + (swsel ^ 1) * 576 + tg * 4, dec_ptr(p.packed, ctl->item[nx] & 0xFF) + tg * 4);
-              }
-              swsel ^= 1;
+              mbar_wait(&sw_full[chain_id * SW_SLOTS + (swj % SW_SLOTS)], (swj / SW_SLOTS) & 1u);
+              if (!F16) named_bar(bar_id, GROUP_THREADS);
+              const float* sw = swbuf + (swj % SW_SLOTS) * 576;
+              ++swj;
               const float2 z = s.zs[pt];
               const float2 zx2 = make_float2(z.x, z.x), zy2 = make_float2(z.y, z.y);
               // mask words for E-B3 (L2 round trip overlaps the G build and the first MMA)
@@ -1005,7 +1007,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
       __threadfence_block();
       mbar_arrive(win_ready);
     }
-    cp_async_wait_all();
 #ifdef VLG_TC_STATS
     if (tg == 0 && blockIdx.x < 1024) g_tc_stats[blockIdx.x * 8 + 4 + chain_id * 2] = w_acc;
 #endif
