@@ -1,15 +1,19 @@
-// tcgen05 (TF32) geodesic step kernel -- the tensor-core variant (<=1e-3 relative on lengths).
+// tcgen05 geodesic step kernel -- the tensor-core variants.
 //
 // Persistent CTAs (one per SM, 608 threads) pull work units -- (curve, chunk of Adam steps) -- from
 // a global queue; a curve's chunks are chained through its omega/m/v in HBM, so a launch of
 // `steps` steps has no tail longer than one chunk.  The two 128-wide decoder layers and their
-// transposes run as tcgen05.mma kind::tf32 with
+// transposes run as tcgen05.mma with
 //   * M = 128 rows = the 128 TMEM lanes,
 //   * the A operand (activations) living in TENSOR MEMORY: the epilogue threads write the
-//     next layer's input back with tcgen05.st, in place of the accumulator they just read,
+//     next layer's input with tcgen05.st after reading the accumulator with tcgen05.ld,
 //   * the B operand (weights) streamed from L2 into per-chain shared-memory rings by the TMA
 //     engine (1-D bulk copies of pre-packed no-swizzle K-major images, mbarrier complete_tx),
-//   * fp32 accumulators in TMEM, read back with tcgen05.ld.
+//   * fp32 accumulators in TMEM.
+// Three operand formats (template parameter FMT, VLG_PRECISION_*):
+//   FMT_TF32   kind::tf32, operands rounded to TF32 (<= 1e-3 relative on lengths)
+//   FMT_F16    kind::f16, fp16 operands: same 11-bit significand, half the MMAs and weight bytes
+//   FMT_F16X3  kind::f16, every operand as hi + lo fp16 pairs, three MMAs per product: fp32-grade
 //
 // ROW COMPACTION.  The MC energy touches, per curve point, only the decoders drawn for the two
 // segments that meet there (<= 2M of K; 3.4 of 10 on average), and the reference's dense
@@ -21,7 +25,8 @@
 // each selected (point, decoder) pair goes through exactly the same arithmetic.
 //
 // Warp roles: warps 0/1 = weight producers of chain 0/1 (one lane each), warp 2 = MMA issuer
-// (one lane), warps 3-10 and 11-18 = two epilogue groups of 8 warps.  Each group owns a "chain"
+// (all lanes run the loop, one elected lane's instructions take effect), warps 3-10 and 11-18 = two
+// epilogue groups of 8 warps.  Each group owns a "chain"
 // of 256 TMEM columns and every other item.  The MMA issuer serves whichever chain has its
 // operand ready, which is why every chain has its own weight ring.  Inside a group two threads
 // share a row (TMEM lane) and split its columns: four epilogue warps per scheduler hide TMEM /
@@ -139,10 +144,6 @@ __device__ __forceinline__ uint32_t relu_tf32(float v) { return __float_as_uint(
 __device__ __forceinline__ void named_bar(int id, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
-__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
