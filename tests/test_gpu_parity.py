@@ -435,3 +435,32 @@ def test_full_config1_1000_steps_final_lengths(vlg, prec, tol):
     final = np.abs(np.sqrt(trace[-1]) / g["final_length_f64"] - 1).max()
     assert final < tol, final
     assert np.abs(model.omega.cpu().numpy() - g["omega_f64"]).max() < 5e-2
+
+
+@pytest.mark.parametrize("prec", ["f16", "f16x3"])
+def test_full_pair_list_sharding_and_modes_agree(vlg, prec):
+    """BASELINE config 3 at its full width (8778 pairs, K=10, M=2, T=2000), size-independent properties:
+    the 8-way shard of the pair list reproduces the single-launch result bit for bit (the work queue hands
+    curves to CTAs in a different order), every energy is finite and positive, and the two fp16 modes agree
+    with each other to the single-term tolerance."""
+    import bench
+    w, a, b, omega, _ = bench.synthetic_workload(bench.N_CURVES)
+    dev = "cuda"
+    dec = vlg.DecoderEnsemble.from_arrays(*[w[k] for k in ("W1", "b1", "W2", "b2", "W3", "b3")], dev)
+    basis, _ = vlg.construct_nullspace_basis(4)
+    t = torch.linspace(0, 1, 2000, device=dev)
+    N, S = bench.N_CURVES, 3
+
+    def run(lo, hi, p):
+        m = vlg.GeodesicSplineBatch(a[lo:hi].to(dev), b[lo:hi].to(dev), basis.to(dev), omega[lo:hi].to(dev), 4)
+        e = vlg.optimize_splines(m, dec, t, S, M=2, seed=4, curve_id0=lo, precision=p)
+        return m.omega, e
+
+    om_full, e_full = run(0, N, prec)
+    assert bool(torch.isfinite(e_full).all()) and float(e_full.min()) > 0
+    from vlg_b200.sharding import shard_range
+    oms, es = zip(*[run(*shard_range(N, r, 8), prec) for r in range(8)])
+    assert torch.equal(torch.cat(oms), om_full) and torch.equal(torch.cat(es), e_full)
+    if prec == "f16":
+        _, e_x3 = run(0, N, "f16x3")
+        assert float((torch.sqrt(e_full / e_x3) - 1).abs().max()) < 2e-3
