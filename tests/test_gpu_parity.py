@@ -464,3 +464,56 @@ def test_full_pair_list_sharding_and_modes_agree(vlg, prec):
     if prec == "f16":
         _, e_x3 = run(0, N, "f16x3")
         assert float((torch.sqrt(e_full / e_x3) - 1).abs().max()) < 2e-3
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tf32", "f16", "f16x3"])
+@pytest.mark.parametrize("T,N,K,M,n_poly", [(513, 150, 7, 2, 4), (2000, 5, 10, 2, 4), (130, 3, 3, 1, 8)])
+def test_kernels_write_only_inside_their_buffers(vlg, prec, T, N, K, M, n_poly):
+    """Guard bands: the workspace is handed over at exactly vlg_workspace_bytes, and it, the curve state and
+    the outputs sit inside larger buffers filled with a pattern; nothing outside the declared extents may
+    change (compute-sanitizer is not available on the GPU pool, this is the bounds check we can run)."""
+    from vlg_b200 import ops
+    rng = np.random.default_rng(T + K)
+    W = dict(W1=rng.normal(size=(K, 128, 2)) * 0.7, b1=rng.normal(size=(K, 128)) * 0.3,
+             W2=rng.normal(size=(K, 128, 128)) * 0.09, b2=rng.normal(size=(K, 128)) * 0.1,
+             W3=rng.normal(size=(K, 50, 128)) * 0.09, b3=rng.normal(size=(K, 50)) * 0.1)
+    g = {k: v.astype(np.float32) for k, v in W.items()}
+    dec = make_decoders(vlg, g, K)
+    basis, _ = vlg.construct_nullspace_basis(n_poly)
+    dev, G, S, Kb = "cuda", 4096, 2, n_poly + 1
+    code = ops.PRECISIONS[prec]
+
+    def guarded(nbytes_or_tensor, dtype=torch.float32):
+        """-> (view of the payload, full byte buffer, payload byte range)"""
+        if isinstance(nbytes_or_tensor, int):
+            nbytes, src = nbytes_or_tensor, None
+        else:
+            src = nbytes_or_tensor.contiguous()
+            nbytes = src.numel() * src.element_size()
+        nbytes_al = (nbytes + 255) // 256 * 256
+        buf = torch.full((G + nbytes_al + G,), 0xA5, dtype=torch.uint8, device=dev)
+        view = buf[G:G + nbytes].view(dtype) if dtype != torch.uint8 else buf[G:G + nbytes]
+        if src is not None:
+            view.copy_(src.to(dev).view(-1))
+        return view, buf, (G, G + nbytes)
+
+    omega0 = torch.tensor(0.1 * rng.normal(size=(N, Kb, 2)), dtype=torch.float32)
+    om, om_buf, om_rng = guarded(omega0)
+    m_, m_buf, m_rng = guarded(torch.zeros(N, Kb, 2))
+    v_, v_buf, v_rng = guarded(torch.zeros(N, Kb, 2))
+    e_, e_buf, e_rng = guarded(torch.zeros(N))
+    tr, tr_buf, tr_rng = guarded(torch.zeros(S, N))
+    nws = ops.workspace_bytes(N, T, n_poly, K, M, code)
+    ws, ws_buf, ws_rng = guarded(int(nws), torch.uint8)
+    a = torch.tensor(rng.uniform(-3, 3, (N, 2)), dtype=torch.float32, device=dev)
+    b = torch.tensor(rng.uniform(-3, 3, (N, 2)), dtype=torch.float32, device=dev)
+    t = torch.linspace(0, 1, T, device=dev)
+    ops.optimize_steps(dec.packed, K, n_poly, M, S, 0, a, b, om.view(N, Kb, 2), m_.view(N, Kb, 2), v_.view(N, Kb, 2),
+                       basis.to(dev).float().contiguous(), t, None, 3, 11, 1e-3, 0.9, 0.999, 1e-8, 1000.0, e_, tr.view(S, N), code,
+                       ws if nws else None)
+    torch.cuda.synchronize()
+    for name, buf, (lo, hi) in (("omega", om_buf, om_rng), ("adam_m", m_buf, m_rng), ("adam_v", v_buf, v_rng),
+                                ("energy", e_buf, e_rng), ("trace", tr_buf, tr_rng), ("workspace", ws_buf, ws_rng)):
+        assert bool((buf[:lo] == 0xA5).all()), f"{name}: write below the buffer"
+        assert bool((buf[hi:] == 0xA5).all()), f"{name}: write above the buffer"
+    assert bool(torch.isfinite(e_).all()) and not torch.equal(om.view(N, Kb, 2).cpu(), omega0)
