@@ -10,7 +10,8 @@ dec = vlg_b200.DecoderEnsemble.from_arrays(*[w[k] for k in ("W1", "b1", "W2", "b
 basis, _ = vlg_b200.construct_nullspace_basis(4)
 t = torch.linspace(0, 1, 2000, device=dev)
 out = {}
-for prec in ("f16", "tf32", "fp32"):
+modes = sys.argv[2].split(",") if len(sys.argv) > 2 else ["f16", "tf32", "fp32"]
+for prec in modes:
     m = vlg_b200.GeodesicSplineBatch(a.to(dev), b.to(dev), basis.to(dev), omega.to(dev), 4)
     vlg_b200.optimize_splines(vlg_b200.GeodesicSplineBatch(a.to(dev), b.to(dev), basis.to(dev), omega.to(dev), 4), dec, t, 1, M=2, seed=0, precision=prec)
     torch.cuda.synchronize(); t0 = time.perf_counter()
@@ -24,7 +25,7 @@ for prec in ("f16", "tf32", "fp32"):
     print(f"{prec:5s}: {bench.N_CURVES} curves x {steps} steps in {dt:7.2f} s -> {bench.N_CURVES * steps / dt:9.0f} spline-steps/s; mean length {out[prec][0].mean():.4f}", flush=True)
 ref = out["fp32"][0]
 res = {"steps": steps, "weights": weights}
-for prec in ("f16", "tf32"):
+for prec in [m_ for m_ in modes if m_ != "fp32"]:
     rel = np.abs(out[prec][0] / ref - 1)
     res[prec] = {"seconds": out[prec][2], "max_rel_length_diff_vs_fp32": float(rel.max()), "mean_rel_length_diff_vs_fp32": float(rel.mean()),
                  "p999": float(np.quantile(rel, 0.999))}
