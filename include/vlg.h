@@ -11,8 +11,10 @@
  *
  * Conventions
  *   - every pointer is a DEVICE pointer on the current CUDA device unless stated;
- *     the caller owns every buffer; nothing is allocated, nothing is synchronised:
- *     work is enqueued on `stream` (a cudaStream_t passed as void*).
+ *     the caller owns every buffer; nothing is allocated, nothing is synchronised
+ *     (vlg_workspace_status is the one documented exception): work is enqueued on
+ *     `stream` (a cudaStream_t passed as void*).  The library keeps no per-buffer state:
+ *     the caller passes the packed ensemble's K and X with every call.
  *   - all arrays are dense, row-major, fp32 unless stated.
  *   - every function returns 0 on success or a negative VLG_ERR_* code; it never throws.
  *   - requires an sm_100 (B200) device: there is no CPU or other-arch fallback.
@@ -31,7 +33,7 @@
 extern "C" {
 #endif
 
-#define VLG_ABI_VERSION 1
+#define VLG_ABI_VERSION 2
 
 enum {
   VLG_OK = 0,
@@ -39,7 +41,17 @@ enum {
   VLG_ERR_UNSUPPORTED = -2,      /* shape outside what the kernels are built for      */
   VLG_ERR_CUDA = -3,             /* a CUDA runtime call failed (see vlg_last_cuda_error) */
   VLG_ERR_DEVICE = -4,           /* current device is not sm_100                      */
-  VLG_ERR_WORKSPACE = -5         /* workspace too small                               */
+  VLG_ERR_WORKSPACE = -5,        /* workspace too small                               */
+  VLG_ERR_NUMERIC = -6           /* vlg_workspace_status: the last launch saw a non-finite energy / omega
+                                    (fp16 operand overflow) or an out-of-range explicit draw          */
+};
+
+/* Status flags a step kernel leaves in its workspace (read back by vlg_workspace_status). */
+enum {
+  VLG_STATUS_BAD_DRAW = 1,  /* an explicit draw was >= K_active (the kernel clamped it to K_active-1) */
+  VLG_STATUS_BAD_PACKED = 4, /* `packed` does not start with a header of the K / X the caller passed */
+  VLG_STATUS_NONFINITE = 2  /* an energy or an updated omega was inf/NaN: with VLG_PRECISION_F16* this is
+                               what an operand beyond the fp16 range (65504) turns into              */
 };
 
 /* Arithmetic used for the two 128-wide decoder layers (and their transposes). */
@@ -82,15 +94,17 @@ size_t vlg_workspace_bytes(int N, int T, int n_poly, int K_active, int M, int pr
  * (158-160), backward to omega (161; decoder weight gradients are not formed), Adam
  * (162; torch defaults, bias correction uses step0+s+1).
  *
- *   packed      from vlg_pack_decoders; the first K_active decoders are used
+ *   packed      from vlg_pack_decoders (of K decoders with X outputs: the caller passes the same
+ *               K and X it packed with); the first K_active decoders are used
  *               (`model.decoder[:k]`, src/eval.py:113)
  *   a, b        [N,2]      end points
  *   omega       [N,Kb,2]   in: current coefficients; out: after `steps` updates
  *   adam_m/v    [N,Kb,2]   in/out Adam moments (zeros for a fresh optimiser)
  *   basis       [4*n_poly,Kb]  from the spline file (never recomputed, SURVEY hard part 7)
  *   t           [T]        the grid torch.linspace(0,1,T) (src/optimize.py:130)
- *   draws       NULL, or uint8 [N,steps,M,2,T-1]: explicit decoder indices
- *               (role 0 = d1 at point t, role 1 = d2 at point t+1; src/optimize.py:57-61).
+ *   draws       NULL, or uint8 [N,steps,M,2,T-1]: explicit decoder indices < K_active
+ *               (role 0 = d1 at point t, role 1 = d2 at point t+1; src/optimize.py:57-61);
+ *               a value >= K_active is clamped and flagged (VLG_STATUS_BAD_DRAW).
  *               NULL -> counter-based Philox4x32-10 stream keyed on
  *               (seed, curve_id0+n, step0+s, m, t): independent of sharding.
  *   energy_last [N]        energy evaluated in the LAST step (before its update), i.e.
@@ -99,13 +113,20 @@ size_t vlg_workspace_bytes(int N, int T, int n_poly, int K_active, int M, int pr
  *   lr..penalty_w are doubles because torch keeps them as Python floats and rounds the
  *   derived scalars (1-beta1, lr/(1-beta1^s), ...) to fp32 only when applying them.
  */
-int vlg_optimize_steps(const void* packed, int K_active, int N, int T, int n_poly, int M,
+int vlg_optimize_steps(const void* packed, int K, int X, int K_active, int N, int T, int n_poly, int M,
                        int steps, int step0, const float* a, const float* b, float* omega,
                        float* adam_m, float* adam_v, const float* basis, const float* t,
                        const uint8_t* draws, uint64_t seed, int64_t curve_id0, double lr,
                        double beta1, double beta2, double eps, double penalty_w,
                        float* energy_last, float* energy_trace, int precision,
                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* Status of the last vlg_optimize_steps / vlg_curve_energy launch that used `workspace`: copies the
+ * status word back and SYNCHRONISES `stream` (the only entry point that does).  *flags (host
+ * pointer, may be NULL) receives the VLG_STATUS_* bits; returns VLG_OK when none is set, else
+ * VLG_ERR_NUMERIC.  Replaces the finite-check a caller of the reference would do on `energy`
+ * (the reference itself never checks: src/optimize.py:164-168 prints whatever it gets). */
+int vlg_workspace_status(const void* workspace, int* flags, void* stream);
 
 /* ---- forward-only evaluation --------------------------------------------------------
  * energy[N]  = compute_energy_mc (src/optimize.py:38-75) for the given omega and draws
@@ -116,7 +137,7 @@ int vlg_optimize_steps(const void* packed, int K_active, int N, int T, int n_pol
  *              compute_geodesic_lengths (optimize_energy_batched.py:42-49).
  * The ensemble "geodesic_length" of src/optimize.py:168 / src/eval.py:127 is sqrt(energy).
  */
-int vlg_curve_energy(const void* packed, int K_active, int N, int T, int n_poly, int M,
+int vlg_curve_energy(const void* packed, int K, int X, int K_active, int N, int T, int n_poly, int M,
                      const float* a, const float* b, const float* omega, const float* basis,
                      const float* t, const uint8_t* draws, uint64_t seed, int64_t curve_id0,
                      int step, float* energy, float* length, int precision, void* workspace,
@@ -126,7 +147,7 @@ int vlg_curve_energy(const void* packed, int K_active, int N, int T, int n_poly,
  * out[g] = || std_k f_k(grid[g]) ||_2 over the first K_active decoders, unbiased std
  * (src/init_splines_ensemble.py:49-51, before the min-max normalisation).  grid [G,2].
  */
-int vlg_ensemble_std_norm(const void* packed, int K_active, int G, const float* grid,
+int vlg_ensemble_std_norm(const void* packed, int K, int X, int K_active, int G, const float* grid,
                           float* out, void* stream);
 
 /* ---- spline evaluation ----------------------------------------------------------------

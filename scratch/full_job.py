@@ -32,3 +32,5 @@ for prec in [m_ for m_ in modes if m_ != "fp32"]:
     print(f"{prec}: final length vs fp32 kernel over {len(ref)} curves: max {rel.max():.2e}, 99.9 % {np.quantile(rel, 0.999):.2e}, mean {rel.mean():.2e}")
 res["fp32"] = {"seconds": out["fp32"][2]}
 open("gpurun_out/full_job.json", "w").write(json.dumps(res, indent=1))
+np.savez_compressed("gpurun_out/full_job_lengths.npz", **{f"len_{k}": v[0].astype(np.float32) for k, v in out.items()},
+                    **{f"omega_{k}": v[1] for k, v in out.items()})

@@ -40,7 +40,7 @@ def plot_geodesic_matrix(spline_blob, output_path, len_type="geodesic", seed=Non
     return mat
 
 
-def run_cov_analysis(seeds, decoder_counts, pairfile, model_dir, data_path, output_plot, steps=300, precision="f16x3",
+def run_cov_analysis(seeds, decoder_counts, pairfile, model_dir, data_path, output_plot, steps=300, precision=None,
                      draw_seed=0):
     """CoV of geodesic lengths across seeds for k = 1..10 decoders (src/eval.py:74-159)."""
     device = torch.device("cuda")
@@ -85,7 +85,7 @@ def main():
     parser.add_argument("--pair-count", type=int, default=133)
     parser.add_argument("--seed", type=int)
     parser.add_argument("--seeds", nargs="*", type=int, default=[12, 123])
-    parser.add_argument("--precision", type=str, default="f16x3", choices=["f16", "f16x3", "tf32", "fp32"])
+    parser.add_argument("--precision", type=str, default=vlg_b200.DEFAULT_PRECISION, choices=["f16", "f16x3", "tf32", "fp32"])
     args = parser.parse_args()
     plot_dir = Path("experiment/plots")
     plot_dir.mkdir(parents=True, exist_ok=True)

@@ -32,7 +32,7 @@ def test_python_binding_covers_the_header(built_lib):
     from vlg_b200 import _lib
     assert sorted(_lib.SIGNATURES) == declared_functions()
     lib = _lib.load()
-    assert lib.vlg_abi_version() == 1
+    assert lib.vlg_abi_version() == 2
     assert lib.vlg_error_string(0) == b"ok"
     assert b"sm_100" in lib.vlg_error_string(-4)
 
@@ -46,14 +46,39 @@ def test_sizes_and_argument_errors_without_gpu(built_lib):
     assert lib.vlg_packed_decoders_bytes(10, 128, 100) == 0    # X too wide
     # fp32 kernel: ReLU-mask scratch per persistent CTA (<= one CTA per curve): whole 2 KB items
     ws = lib.vlg_workspace_bytes(45, 2000, 4, 10, 2, 0)
-    assert ws > 0 and ws % (45 * 2048) == 0
+    assert ws > 256 and (ws - 256) % (45 * 2048) == 0   # 256-byte status header + items
     assert lib.vlg_workspace_bytes(45, 2000, 4, 10, 2, 3) == lib.vlg_workspace_bytes(45, 2000, 4, 10, 2, 1) > 0
     # null pointers are rejected before any CUDA call
-    rc = lib.vlg_optimize_steps(None, 10, 4, 2000, 4, 2, 1, 0, None, None, None, None, None, None, None, None,
+    rc = lib.vlg_optimize_steps(None, 10, 50, 10, 4, 2000, 4, 2, 1, 0, None, None, None, None, None, None, None, None,
                                 0, 0, 1e-3, 0.9, 0.999, 1e-8, 1000.0, None, None, 0, None, 0, None)
     assert rc == -1
-    assert lib.vlg_curve_energy(None, 1, 1, 2, 1, 1, None, None, None, None, None, None, 0, 0, 0, None, None, 0,
+    assert lib.vlg_workspace_status(None, None, None) == -1
+    assert lib.vlg_curve_energy(None, 1, 50, 1, 1, 2, 1, 1, None, None, None, None, None, None, 0, 0, 0, None, None, 0,
                                 None, 0, None) == -1
+
+
+def test_selftest_kernels_are_not_in_the_product_library(built_lib):
+    import subprocess
+    import vlg_b200
+    syms = subprocess.run(["nm", "-D", "--defined-only", str(built_lib)], capture_output=True, text=True).stdout
+    assert "vlg_selftest" not in syms and "mma_rate" not in syms
+    st = vlg_b200.build.build_selftest()
+    syms = subprocess.run(["nm", "-D", "--defined-only", str(st)], capture_output=True, text=True).stdout
+    for name in vlg_b200._lib.SELFTEST_SIGNATURES:
+        assert name in syms
+
+
+def test_draws_are_range_checked_on_the_host(built_lib):
+    import torch
+    from vlg_b200 import api
+    ok = torch.randint(0, 3, (2, 2, 2, 9, 4))
+    assert api._prep_draws(ok, 4, 2, 2, 10, "cpu", 3).shape == (4, 2, 2, 2, 9)
+    with pytest.raises(api._lib.VlgError):
+        api._prep_draws(ok, 4, 2, 2, 10, "cpu", 2)          # a draw of 2 with two active decoders
+    with pytest.raises(api._lib.VlgError):
+        api._prep_draws(ok - 1, 4, 2, 2, 10, "cpu", 3)      # negative
+    with pytest.raises(api._lib.VlgError):
+        api._prep_draws(ok.float(), 4, 2, 2, 10, "cpu", 3)  # not an integer tensor
 
 
 def test_cpu_tensors_are_rejected_loudly(built_lib):

@@ -251,6 +251,81 @@ def test_errors_are_loud(vlg):
         vlg.optimize_splines(model, dec, t.cpu(), 1, M=1, precision="fp32")  # CPU tensor
     with pytest.raises(vlg.VlgError):
         vlg.optimize_splines(model, dec, t, 1, M=1, draws=np.zeros((1, 1, 2, 5, 5)), precision="fp32")
+    N = g["a"].shape[0]
+    with pytest.raises(vlg.VlgError):                                        # draw index 4 with 4 active decoders
+        vlg.optimize_splines(make_model(vlg, g), dec, t, 1, M=1, draws=np.full((1, 1, 2, 129, N), 4), precision="fp32")
+    with pytest.raises(vlg.VlgError):
+        vlg.optimize_splines(make_model(vlg, g), dec, t, 1, M=1, precision="bf16")
+
+
+@pytest.mark.parametrize("prec", ["fp32", "f16", "f16x3", "tf32"])
+def test_kernel_status_word_reports_bad_draws_and_overflow(vlg, prec):
+    """The C ABI itself (no host-side validation): an out-of-range explicit draw is clamped and flagged, and
+    a non-finite result (fp16 operand overflow) is flagged -- vlg_workspace_status returns VLG_ERR_NUMERIC."""
+    from vlg_b200 import ops, api
+    g = Hh.load("synth_np4_T130")
+    N, T, K, M = g["a"].shape[0], 130, 4, 2
+    dec = make_decoders(vlg, g, K)
+    code = ops.PRECISIONS[prec]
+    t = torch.linspace(0, 1, T, device="cuda")
+
+    def launch(dec_, draws):
+        m = make_model(vlg, g)
+        ws = api._workspace(m, dec_, T, M, code)
+        e = torch.empty(N, device="cuda")
+        ops.optimize_steps(dec_.packed, dec_.K, dec_.X, len(dec_), 4, M, 1, 0, m.a, m.b, m.omega, m.adam_m, m.adam_v,
+                           m.basis, t, draws, 0, 0, 1e-3, 0.9, 0.999, 1e-8, 1000.0, e, None, code, ws)
+        return ops.workspace_status(ws), e
+
+    assert launch(dec, None)[0] == 0
+    bad = torch.full((N, 1, M, 2, T - 1), 200, dtype=torch.uint8, device="cuda")
+    flags, e = launch(dec, bad)
+    assert flags & ops.STATUS_BAD_DRAW and bool(torch.isfinite(e).all())     # clamped to decoder K-1, memory-safe
+    # decoders whose hidden activations exceed the fp16 range
+    arrs = {k: v.copy() for k, v in Hh.decoder_arrays(g).items()}
+    arrs["W2"] = arrs["W2"] * 3.0e4
+    big = vlg.DecoderEnsemble.from_arrays(*[arrs[k] for k in Hh.DEC_KEYS], "cuda")[:K]
+    flags, e = launch(big, None)
+    if prec in ("f16", "f16x3"):
+        assert flags & ops.STATUS_NONFINITE
+        with pytest.raises(vlg.VlgError, match="fp16 range"):
+            vlg.optimize_splines(make_model(vlg, g), big, t, 1, M=M, precision=prec)
+    else:
+        assert flags == 0 and bool(torch.isfinite(e).all())
+
+
+@pytest.mark.parametrize("tc", ["tf32", "f16", "f16x3"])
+def test_split_row_lists_are_deterministic(vlg, tc):
+    """Few decoders and long windows: every decoder is drawn by far more than 128 points of a window, so
+    each row list is split into several 128-row items that run on DIFFERENT chains.  Item membership is
+    by point order (not by thread arrival order), so repeated runs, a different launch shape and any
+    sharding give bit-identical results (the round-1 kernel failed exactly this)."""
+    rng = np.random.default_rng(7)
+    K, T, N, S = 2, 600, 300, 3
+    W = dict(W1=rng.normal(size=(K, 128, 2)) * 0.7, b1=rng.normal(size=(K, 128)) * 0.3,
+             W2=rng.normal(size=(K, 128, 128)) * 0.09, b2=rng.normal(size=(K, 128)) * 0.1,
+             W3=rng.normal(size=(K, 50, 128)) * 0.09, b3=rng.normal(size=(K, 50)) * 0.1)
+    dec = make_decoders(vlg, {k: v.astype(np.float32) for k, v in W.items()}, K)
+    basis, _ = vlg.construct_nullspace_basis(4)
+    a = torch.tensor(rng.uniform(-3, 3, (N, 2)), dtype=torch.float32)
+    b = torch.tensor(rng.uniform(-3, 3, (N, 2)), dtype=torch.float32)
+    om = torch.tensor(0.1 * rng.normal(size=(N, 5, 2)), dtype=torch.float32)
+    t = torch.linspace(0, 1, T, device="cuda")
+
+    def run(lo, hi):
+        m = vlg.GeodesicSplineBatch(a[lo:hi].cuda(), b[lo:hi].cuda(), basis.cuda(), om[lo:hi].cuda(), 4)
+        e = vlg.optimize_splines(m, dec, t, S, M=2, seed=9, curve_id0=lo, precision=tc)
+        return m.omega.clone(), e.clone()
+
+    ref_om, ref_e = run(0, N)
+    assert bool(torch.isfinite(ref_e).all())
+    for _ in range(4):                                   # run to run
+        o, e = run(0, N)
+        assert torch.equal(o, ref_om) and torch.equal(e, ref_e)
+    for parts in (2, 7):                                 # shard to shard
+        from vlg_b200.sharding import shard_range
+        oms, es = zip(*[run(*shard_range(N, r, parts)) for r in range(parts)])
+        assert torch.equal(torch.cat(oms), ref_om) and torch.equal(torch.cat(es), ref_e)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -437,7 +512,7 @@ def test_full_config1_1000_steps_final_lengths(vlg, prec, tol):
     assert np.abs(model.omega.cpu().numpy() - g["omega_f64"]).max() < 5e-2
 
 
-@pytest.mark.parametrize("prec", ["f16", "f16x3"])
+@pytest.mark.parametrize("prec", ["f16", "f16x3", "tf32"])
 def test_full_pair_list_sharding_and_modes_agree(vlg, prec):
     """BASELINE config 3 at its full width (8778 pairs, K=10, M=2, T=2000), size-independent properties:
     the 8-way shard of the pair list reproduces the single-launch result bit for bit (the work queue hands
@@ -508,7 +583,7 @@ def test_kernels_write_only_inside_their_buffers(vlg, prec, T, N, K, M, n_poly):
     a = torch.tensor(rng.uniform(-3, 3, (N, 2)), dtype=torch.float32, device=dev)
     b = torch.tensor(rng.uniform(-3, 3, (N, 2)), dtype=torch.float32, device=dev)
     t = torch.linspace(0, 1, T, device=dev)
-    ops.optimize_steps(dec.packed, K, n_poly, M, S, 0, a, b, om.view(N, Kb, 2), m_.view(N, Kb, 2), v_.view(N, Kb, 2),
+    ops.optimize_steps(dec.packed, dec.K, dec.X, K, n_poly, M, S, 0, a, b, om.view(N, Kb, 2), m_.view(N, Kb, 2), v_.view(N, Kb, 2),
                        basis.to(dev).float().contiguous(), t, None, 3, 11, 1e-3, 0.9, 0.999, 1e-8, 1000.0, e_, tr.view(S, N), code,
                        ws if nws else None)
     torch.cuda.synchronize()

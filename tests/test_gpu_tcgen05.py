@@ -27,7 +27,7 @@ def tf32_rn(x):
 
 def run(N, K, mn, split3, seed=0):
     from vlg_b200 import _lib
-    lib = _lib.load()
+    lib = _lib.load_selftest()
     g = torch.Generator().manual_seed(seed)
     B = torch.randn(N, K, generator=g)
     KK = N if mn else K
@@ -48,7 +48,7 @@ def run(N, K, mn, split3, seed=0):
 
 @pytest.mark.parametrize("N,K", [(128, 128), (64, 128), (128, 64), (16, 16)])
 @pytest.mark.parametrize("mn", [0])
-def test_tf32_mma_matches_matmul(built_lib, N, K, mn):
+def test_tf32_mma_matches_matmul(selftest_lib, N, K, mn):
     D, ref = run(N, K, mn, 0)
     err = (D - ref).abs().max().item() / ref.abs().max().item()
     assert err < 3e-3, err   # tf32 inputs (10-bit mantissa), fp32 accumulate
@@ -56,17 +56,17 @@ def test_tf32_mma_matches_matmul(built_lib, N, K, mn):
 
 @pytest.mark.parametrize("N,K", [(128, 128), (64, 128)])
 @pytest.mark.parametrize("mn", [0])
-def test_3xtf32_is_fp32_grade(built_lib, N, K, mn):
+def test_3xtf32_is_fp32_grade(selftest_lib, N, K, mn):
     D, ref = run(N, K, mn, 1)
     err = (D - ref).abs().max().item() / ref.abs().max().item()
     assert err < 2e-5, err
 
 
 @pytest.mark.parametrize("N,K", [(128, 128), (64, 128), (128, 64), (16, 16)])
-def test_f16_mma_matches_matmul(built_lib, N, K):
+def test_f16_mma_matches_matmul(selftest_lib, N, K):
     """kind::f16: fp16 pairs in TMEM (even k in the low half), fp16 image img16[(k/8)*N + n][k%8]."""
     from vlg_b200 import _lib
-    lib = _lib.load()
+    lib = _lib.load_selftest()
     g = torch.Generator().manual_seed(N + K)
     B = torch.randn(N, K, generator=g)
     A = torch.randn(128, K, generator=g)

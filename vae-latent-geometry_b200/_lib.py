@@ -23,22 +23,24 @@ SIGNATURES = {
     "vlg_packed_decoders_bytes": (c_size_t, [c_int, c_int, c_int]),
     "vlg_pack_decoders": (c_int, [c_void_p] * 6 + [c_int, c_int, c_int, c_void_p, c_void_p]),
     "vlg_workspace_bytes": (c_size_t, [c_int] * 6),
-    "vlg_optimize_steps": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,  # packed..step0
+    "vlg_workspace_status": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "vlg_optimize_steps": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,  # packed K X ..step0
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,         # a b omega m v
                                    c_void_p, c_void_p, c_void_p, c_uint64, c_int64,           # basis t draws seed id0
                                    c_double, c_double, c_double, c_double, c_double,          # lr b1 b2 eps pen
                                    c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
-    "vlg_curve_energy": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int,
+    "vlg_curve_energy": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_uint64, c_int64, c_int, c_void_p, c_void_p, c_int, c_void_p,
                                  c_size_t, c_void_p]),
-    "vlg_ensemble_std_norm": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "vlg_ensemble_std_norm": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "vlg_spline_points": (c_int, [c_int, c_int, c_int] + [c_void_p] * 7),
     "vlg_fit_splines": (c_int, [c_int, c_int, c_int] + [c_void_p] * 6),
 }
 
 
-# test hooks declared in include/vlg_selftest.h
+# test hooks declared in include/vlg_selftest.h; they live in libvlg_b200_selftest.so (tests only)
+SELFTEST_LIB_PATH = Path(__file__).resolve().parent / "libvlg_b200_selftest.so"
 SELFTEST_SIGNATURES = {
     "vlg_selftest_umma": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "vlg_selftest_umma_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
@@ -59,14 +61,32 @@ def load():
             f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
             "vlg_b200 has no CPU / PyTorch fallback.")
     lib = ctypes.CDLL(str(LIB_PATH))
-    for name, (res, args) in {**SIGNATURES, **SELFTEST_SIGNATURES}.items():
+    for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.vlg_abi_version() != 1:
+    if lib.vlg_abi_version() != 2:
         raise VlgError("libvlg_b200.so ABI version mismatch")
     _lib = lib
     return lib
+
+
+_selftest = None
+
+
+def load_selftest():
+    """Load the test-only library (built by vlg_b200.build.build_selftest)."""
+    global _selftest
+    if _selftest is None:
+        if not SELFTEST_LIB_PATH.exists():
+            raise VlgError(f"{SELFTEST_LIB_PATH} is missing: vlg_b200.build.build_selftest()")
+        lib = ctypes.CDLL(str(SELFTEST_LIB_PATH))
+        for name, (res, args) in SELFTEST_SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _selftest = lib
+    return _selftest
 
 
 def check(rc: int, what: str) -> None:

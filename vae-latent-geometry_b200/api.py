@@ -114,8 +114,9 @@ class GeodesicSplineBatch:
     __call__ = forward
 
 
-def _prep_draws(draws, N: int, steps: int, M: int, T: int, device) -> Optional[torch.Tensor]:
-    """Reference layout [S,M,2,T-1,N] (any int dtype) -> kernel layout uint8 [N,S,M,2,T-1]."""
+def _prep_draws(draws, N: int, steps: int, M: int, T: int, device, K_active: int) -> Optional[torch.Tensor]:
+    """Reference layout [S,M,2,T-1,N] (any int dtype) -> kernel layout uint8 [N,S,M,2,T-1].
+    Values must be decoder indices 0 <= d < K_active (torch.randint(0, K, ...), src/optimize.py:57-58)."""
     if draws is None:
         return None
     d = torch.as_tensor(draws)
@@ -123,53 +124,95 @@ def _prep_draws(draws, N: int, steps: int, M: int, T: int, device) -> Optional[t
         d = d[None]
     if tuple(d.shape) != (steps, M, 2, T - 1, N):
         raise _lib.VlgError(f"draws must have shape {(steps, M, 2, T - 1, N)}, got {tuple(d.shape)}")
+    if d.is_floating_point() or d.dtype == torch.bool:
+        raise _lib.VlgError(f"draws must be an integer tensor, got {d.dtype}")
+    if d.numel():
+        lo, hi = int(d.min()), int(d.max())
+        if lo < 0 or hi >= K_active:
+            raise _lib.VlgError(f"draws must lie in [0, {K_active}) for {K_active} active decoders, got [{lo}, {hi}]")
     return d.to(device=device, dtype=torch.uint8).permute(4, 0, 1, 2, 3).contiguous()
 
 
 TC_MAX_M, TC_MAX_K = 2, 64   # limits of the tensor-core kernel (csrc/vlg_tc.cu)
 
+# The ONE default arithmetic of the package, the drop-in CLIs (src/optimize.py, src/eval.py) and bench.py.
+DEFAULT_PRECISION = "f16x3"
 
-def _resolve_precision(precision: str, decoders, M: int) -> int:
-    """'tf32' falls back to the fp32 CUDA-core kernel for shapes the tensor-core kernel is not built for
-    (M > 2 MC samples or more than 64 decoders) and for a single active decoder, where TF32 cannot
-    resolve the tiny adjacent-point differences (SURVEY hard part 1).  Still a GPU kernel -- there is no
-    CPU path."""
-    if precision in ("tf32", "f16", "f16x3", "tf32x3") and (M > TC_MAX_M or len(decoders) > TC_MAX_K):
-        import warnings
+
+def _resolve_precision(precision: Optional[str], decoders, M: int) -> int:
+    """None -> DEFAULT_PRECISION.  Tensor-core precisions fall back to the fp32 CUDA-core kernel for shapes
+    the tensor-core kernel is not built for (M > 2 MC samples or more than 64 decoders); the single-term
+    ones ('tf32', 'f16': 11-bit operands) also for a single active decoder, where they cannot resolve the tiny
+    adjacent-point differences (SURVEY hard part 1; 'f16x3' can).  Still a GPU kernel -- there is no CPU
+    path."""
+    import warnings
+    if precision is None:
+        precision = DEFAULT_PRECISION
+    if precision not in ops.PRECISIONS:
+        raise _lib.VlgError(f"unknown precision {precision!r}; choose from {sorted(ops.PRECISIONS)}")
+    if precision != "fp32" and (M > TC_MAX_M or len(decoders) > TC_MAX_K):
         warnings.warn(f"tensor-core kernel supports M <= {TC_MAX_M}, K <= {TC_MAX_K}; using the fp32 kernel")
+        precision = "fp32"
+    if precision in ("tf32", "f16") and len(decoders) == 1:
+        warnings.warn("single active decoder: 11-bit tensor-core operands cannot resolve adjacent-point "
+                      "differences; using the fp32 kernel (f16x3 is the tensor-core option here)")
         precision = "fp32"
     return ops.PRECISIONS[precision]
 
 
 def _workspace(model, decoders, T, M, precision):
-    n = ops.workspace_bytes(model.omega.shape[0], T, model.n_poly, len(decoders), M, precision)
-    return torch.empty(n, dtype=torch.uint8, device=model.omega.device) if n else None
+    with torch.cuda.device(model.omega.device):   # grid sizing queries the SM count of the current device
+        n = ops.workspace_bytes(model.omega.shape[0], T, model.n_poly, len(decoders), M, precision)
+    return torch.empty(max(n, 256), dtype=torch.uint8, device=model.omega.device)
+
+
+def _raise_on_status(ws: torch.Tensor, what: str) -> None:
+    flags = ops.workspace_status(ws)
+    if flags == 0:
+        return
+    why = []
+    if flags & ops.STATUS_BAD_DRAW:
+        why.append("an explicit draw was >= the number of active decoders")
+    if flags & ops.STATUS_BAD_PACKED:
+        why.append("the packed decoder buffer does not match its K / X")
+    if flags & ops.STATUS_NONFINITE:
+        why.append("non-finite energy or omega (with f16 / f16x3: a decoder activation or gradient beyond the "
+                   "fp16 range 65504 -- use precision='tf32' or 'fp32')")
+    raise _lib.VlgError(f"{what}: " + "; ".join(why))
 
 
 def optimize_splines(model: GeodesicSplineBatch, decoders: DecoderEnsemble, t_vals: torch.Tensor, steps: int,
                      M: int = 2, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
                      penalty_weight: float = 1000.0, draws=None, seed: int = 0, curve_id0: int = 0,
-                     precision: str = "tf32", return_trace: bool = False):
+                     precision: Optional[str] = None, return_trace: bool = False, check: bool = True):
     """`steps` iterations of the loop at src/optimize.py:155-162 for every curve of `model`
     (fresh Adam state unless the model already stepped).  Returns the energy evaluated in the
-    last step [N] (src/optimize.py:168) and, optionally, the per-step energies [steps,N]."""
+    last step [N] (src/optimize.py:168) and, optionally, the per-step energies [steps,N].
+    check=True reads the kernel's status word back after the launch (one stream synchronisation) and
+    raises VlgError on a non-finite result (fp16 operand overflow) instead of returning garbage."""
     N = model.omega.shape[0]
     T = t_vals.shape[0]
     prec = _resolve_precision(precision, decoders, M)
     dev = model.omega.device
     energy = torch.empty(N, dtype=torch.float32, device=dev)
     trace = torch.empty((steps, N), dtype=torch.float32, device=dev) if return_trace else None
-    ops.optimize_steps(decoders.packed, len(decoders), model.n_poly, M, steps, model.step_count, model.a, model.b,
+    if steps <= 0:
+        raise _lib.VlgError("steps must be positive")
+    ws = _workspace(model, decoders, T, M, prec)
+    ops.optimize_steps(decoders.packed, decoders.K, decoders.X, len(decoders), model.n_poly, M, steps,
+                       model.step_count, model.a, model.b,
                        model.omega, model.adam_m, model.adam_v, model.basis, t_vals.contiguous().float(),
-                       _prep_draws(draws, N, steps, M, T, dev), seed, curve_id0, lr, betas[0], betas[1], eps,
-                       penalty_weight, energy, trace, prec, _workspace(model, decoders, T, M, prec))
+                       _prep_draws(draws, N, steps, M, T, dev, len(decoders)), seed, curve_id0, lr, betas[0],
+                       betas[1], eps, penalty_weight, energy, trace, prec, ws)
     model.step_count += steps
+    if check:
+        _raise_on_status(ws, "optimize_splines")
     return (energy, trace) if return_trace else energy
 
 
 def compute_energy_mc(model: GeodesicSplineBatch, decoders: DecoderEnsemble, t_vals: torch.Tensor, M: int = 2,
                       draws=None, seed: int = 0, step: int = 0, curve_id0: int = 0, precision: str = "fp32",
-                      return_length: bool = False):
+                      return_length: bool = False, check: bool = True):
     """MC ensemble curve energy [N] (src/optimize.py:38-75), forward only."""
     N = model.omega.shape[0]
     T = t_vals.shape[0]
@@ -177,9 +220,13 @@ def compute_energy_mc(model: GeodesicSplineBatch, decoders: DecoderEnsemble, t_v
     dev = model.omega.device
     energy = torch.empty(N, dtype=torch.float32, device=dev)
     length = torch.empty(N, dtype=torch.float32, device=dev) if return_length else None
-    ops.curve_energy(decoders.packed, len(decoders), model.n_poly, M, model.a, model.b, model.omega, model.basis,
-                     t_vals.contiguous().float(), _prep_draws(draws, N, 1, M, T, dev), seed, curve_id0, step,
-                     energy, length, prec, _workspace(model, decoders, T, M, prec))
+    ws = _workspace(model, decoders, T, M, prec)
+    ops.curve_energy(decoders.packed, decoders.K, decoders.X, len(decoders), model.n_poly, M, model.a, model.b,
+                     model.omega, model.basis, t_vals.contiguous().float(),
+                     _prep_draws(draws, N, 1, M, T, dev, len(decoders)), seed, curve_id0, step,
+                     energy, length, prec, ws)
+    if check:
+        _raise_on_status(ws, "compute_energy_mc")
     return (energy, length) if return_length else energy
 
 
@@ -207,7 +254,7 @@ def ensemble_std_norm(decoders: DecoderEnsemble, grid: torch.Tensor) -> torch.Te
     """|| std over decoders of f_k(grid) ||_2 (src/init_splines_ensemble.py:49-51)."""
     grid = grid.contiguous().float()
     out = torch.empty(grid.shape[0], dtype=torch.float32, device=grid.device)
-    ops.ensemble_std_norm(decoders.packed, len(decoders), grid, out)
+    ops.ensemble_std_norm(decoders.packed, decoders.K, decoders.X, len(decoders), grid, out)
     return out
 
 

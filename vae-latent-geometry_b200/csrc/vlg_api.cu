@@ -4,8 +4,6 @@
 #include <stdio.h>
 #include <string.h>
 
-#include <mutex>
-
 #include "vlg_common.cuh"
 #include "vlg_kernels.h"
 
@@ -29,72 +27,16 @@ int check_device() {
   return VLG_OK;
 }
 
-int read_header(const void* packed, vlg::PackedHeader* h, cudaStream_t stream) {
-  cudaError_t e = cudaMemcpyAsync(h, packed, sizeof(*h), cudaMemcpyDeviceToHost, stream);
-  if (e != cudaSuccess) return cuda_fail(e);
-  e = cudaStreamSynchronize(stream);
-  if (e != cudaSuccess) return cuda_fail(e);
-  if (h->magic != vlg::PACK_MAGIC || h->Hdim != vlg::H || h->dec_floats != uint32_t(vlg::DEC_FLOATS))
-    return VLG_ERR_INVALID_ARGUMENT;
-  return VLG_OK;
-}
-
-// The packed header is tiny and immutable after packing; cache (pointer -> K, X) so the
-// hot entry points do not synchronise.  vlg_pack_decoders refreshes the entry.
-struct HeaderCacheEntry {
-  const void* ptr;
-  int K, X;
-};
-constexpr int kCacheSize = 64;
-HeaderCacheEntry g_cache[kCacheSize];
-int g_cache_n = 0;
-int g_cache_next = 0;
-std::mutex g_cache_mu;
-
-void cache_put(const void* ptr, int K, int X) {
-  std::lock_guard<std::mutex> lock(g_cache_mu);
-  for (int i = 0; i < g_cache_n; ++i)
-    if (g_cache[i].ptr == ptr) {
-      g_cache[i].K = K;
-      g_cache[i].X = X;
-      return;
-    }
-  g_cache[g_cache_next] = {ptr, K, X};
-  g_cache_next = (g_cache_next + 1) % kCacheSize;
-  if (g_cache_n < kCacheSize) ++g_cache_n;
-}
-
-int lookup_packed(const void* packed, int* K, int* X, cudaStream_t stream) {
-  {
-    std::lock_guard<std::mutex> lock(g_cache_mu);
-    for (int i = 0; i < g_cache_n; ++i)
-      if (g_cache[i].ptr == packed) {
-        *K = g_cache[i].K;
-        *X = g_cache[i].X;
-        return VLG_OK;
-      }
-  }
-  vlg::PackedHeader h;
-  int rc = read_header(packed, &h, stream);
-  if (rc != VLG_OK) return rc;
-  cache_put(packed, h.K, h.X);
-  *K = h.K;
-  *X = h.X;
-  return VLG_OK;
-}
-
-int fill_params(vlg::StepParams* p, const void* packed, int K_active, int N, int T, int n_poly, int M, int precision,
-                cudaStream_t stream) {
+int fill_params(vlg::StepParams* p, const void* packed, int K, int X, int K_active, int N, int T, int n_poly, int M,
+                int precision) {
   if (!packed || N <= 0 || T < 2 || n_poly < 1 || M < 1 || K_active < 1) return VLG_ERR_INVALID_ARGUMENT;
   if (n_poly > vlg::MAX_NPOLY || M > vlg::MAX_M || K_active > 254) return VLG_ERR_UNSUPPORTED;
   if (precision < VLG_PRECISION_FP32 || precision > VLG_PRECISION_F16) return VLG_ERR_INVALID_ARGUMENT;
-  int K = 0, X = 0;
-  int rc = lookup_packed(packed, &K, &X, stream);
-  if (rc != VLG_OK) return rc;
-  if (K_active > K) return VLG_ERR_INVALID_ARGUMENT;
+  if (vlg_packed_decoders_bytes(K, vlg::H, X) == 0 || K_active > K) return VLG_ERR_INVALID_ARGUMENT;
   memset(p, 0, sizeof(*p));
   p->packed = packed;
   p->K = K_active;
+  p->K_total = K;
   p->X = X;
   p->N = N;
   p->T = T;
@@ -130,6 +72,7 @@ const char* vlg_error_string(int code) {
     case VLG_ERR_CUDA: return "CUDA error (see vlg_last_cuda_error)";
     case VLG_ERR_DEVICE: return "current device is not an sm_100 (B200) GPU";
     case VLG_ERR_WORKSPACE: return "workspace too small";
+    case VLG_ERR_NUMERIC: return "non-finite energy/omega (fp16 operand overflow?) or out-of-range draw in the last launch";
     default: return "unknown error";
   }
 }
@@ -151,9 +94,7 @@ int vlg_pack_decoders(const float* W1, const float* b1, const float* W2, const f
   int rc = check_device();
   if (rc != VLG_OK) return rc;
   cudaError_t e = vlg::launch_pack(W1, b1, W2, b2, W3, b3, K, X, packed, static_cast<cudaStream_t>(stream));
-  if (e != cudaSuccess) return cuda_fail(e);
-  cache_put(packed, K, X);
-  return VLG_OK;
+  return e == cudaSuccess ? VLG_OK : cuda_fail(e);
 }
 
 size_t vlg_workspace_bytes(int N, int T, int n_poly, int K_active, int M, int precision) {
@@ -162,7 +103,7 @@ size_t vlg_workspace_bytes(int N, int T, int n_poly, int K_active, int M, int pr
   return vlg::tc_workspace_bytes(N, T, K_active, M);
 }
 
-int vlg_optimize_steps(const void* packed, int K_active, int N, int T, int n_poly, int M, int steps, int step0,
+int vlg_optimize_steps(const void* packed, int K, int X, int K_active, int N, int T, int n_poly, int M, int steps, int step0,
                        const float* a, const float* b, float* omega, float* adam_m, float* adam_v,
                        const float* basis, const float* t, const uint8_t* draws, uint64_t seed, int64_t curve_id0,
                        double lr, double beta1, double beta2, double eps, double penalty_w, float* energy_last,
@@ -174,7 +115,7 @@ int vlg_optimize_steps(const void* packed, int K_active, int N, int T, int n_pol
   if (rc != VLG_OK) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   vlg::StepParams p;
-  rc = fill_params(&p, packed, K_active, N, T, n_poly, M, precision, st);
+  rc = fill_params(&p, packed, K, X, K_active, N, T, n_poly, M, precision);
   if (rc != VLG_OK) return rc;
   if (workspace_bytes < vlg_workspace_bytes(N, T, n_poly, K_active, M, precision)) return VLG_ERR_WORKSPACE;
   p.steps = steps;
@@ -204,7 +145,20 @@ int vlg_optimize_steps(const void* packed, int K_active, int N, int T, int n_pol
   return dispatch(p, true, st);
 }
 
-int vlg_curve_energy(const void* packed, int K_active, int N, int T, int n_poly, int M, const float* a,
+int vlg_workspace_status(const void* workspace, int* flags, void* stream) {
+  if (!workspace) return VLG_ERR_INVALID_ARGUMENT;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  unsigned int word = 0;
+  // word [1] of the workspace header of both step kernels (zeroed by their launchers)
+  cudaError_t e = cudaMemcpyAsync(&word, static_cast<const unsigned int*>(workspace) + 1, sizeof(word),
+                                  cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return cuda_fail(e);
+  if (flags) *flags = int(word);
+  return word == 0 ? VLG_OK : VLG_ERR_NUMERIC;
+}
+
+int vlg_curve_energy(const void* packed, int K, int X, int K_active, int N, int T, int n_poly, int M, const float* a,
                      const float* b, const float* omega, const float* basis, const float* t, const uint8_t* draws,
                      uint64_t seed, int64_t curve_id0, int step, float* energy, float* length, int precision,
                      void* workspace, size_t workspace_bytes, void* stream) {
@@ -213,7 +167,7 @@ int vlg_curve_energy(const void* packed, int K_active, int N, int T, int n_poly,
   if (rc != VLG_OK) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   vlg::StepParams p;
-  rc = fill_params(&p, packed, K_active, N, T, n_poly, M, precision, st);
+  rc = fill_params(&p, packed, K, X, K_active, N, T, n_poly, M, precision);
   if (rc != VLG_OK) return rc;
   if (workspace_bytes < vlg_workspace_bytes(N, T, n_poly, K_active, M, precision)) return VLG_ERR_WORKSPACE;
   p.steps = 1;
@@ -233,15 +187,13 @@ int vlg_curve_energy(const void* packed, int K_active, int N, int T, int n_poly,
   return dispatch(p, false, st);
 }
 
-int vlg_ensemble_std_norm(const void* packed, int K_active, int G, const float* grid, float* out, void* stream) {
+int vlg_ensemble_std_norm(const void* packed, int K, int X, int K_active, int G, const float* grid, float* out,
+                          void* stream) {
   if (!packed || !grid || !out || G <= 0 || K_active < 1) return VLG_ERR_INVALID_ARGUMENT;
+  if (vlg_packed_decoders_bytes(K, vlg::H, X) == 0 || K_active > K) return VLG_ERR_INVALID_ARGUMENT;
   int rc = check_device();
   if (rc != VLG_OK) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  int K = 0, X = 0;
-  rc = lookup_packed(packed, &K, &X, st);
-  if (rc != VLG_OK) return rc;
-  if (K_active > K) return VLG_ERR_INVALID_ARGUMENT;
   cudaError_t e = vlg::launch_std_norm(packed, K_active, X, G, grid, out, st);
   return e == cudaSuccess ? VLG_OK : cuda_fail(e);
 }

@@ -69,6 +69,12 @@ constexpr int OFF_W2T_HL = OFF_W3T_HL + XP * H / 2;
 constexpr int DEC_FLOATS = OFF_W2T_HL + H * H / 2;
 static_assert(DEC_FLOATS % 64 == 0 && OFF_W2_UMMA % 4 == 0, "images must stay 16-byte aligned");
 
+// device-side check of the header against what the caller said it packed (flags VLG_STATUS_BAD_PACKED = 4)
+__device__ __forceinline__ bool packed_header_ok(const void* packed, int K_total, int X) {
+  const PackedHeader* h = reinterpret_cast<const PackedHeader*>(packed);
+  return h->magic == PACK_MAGIC && h->K == K_total && h->X == X && h->Hdim == H && h->dec_floats == uint32_t(DEC_FLOATS);
+}
+
 __host__ __device__ inline const float* dec_ptr(const void* packed, int k) {
   return reinterpret_cast<const float*>(reinterpret_cast<const char*>(packed) + sizeof(PackedHeader)) +
          size_t(k) * DEC_FLOATS;

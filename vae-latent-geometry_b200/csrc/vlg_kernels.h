@@ -4,11 +4,14 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include "../../include/vlg.h"
+
 namespace vlg {
 
 struct StepParams {
   const void* packed;
   int K, X;                    // active decoders, output width
+  int K_total;                 // decoders in `packed`
   int N, T, n_poly, Kb, M;
   int steps, step0;
   int unit_steps;              // Adam steps per work unit (set by the tensor-core launcher)

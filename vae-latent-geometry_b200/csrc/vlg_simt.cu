@@ -200,7 +200,7 @@ size_t simt_smem_bytes(int T, int K, int M) {
 size_t simt_workspace_bytes(int N, int T, int K, int M) {
   const int W = simt_window_points(T, K, M);
   if (W == 0) return 0;
-  return size_t(simt_grid(N)) * simt_max_items(W, K, M) * 2048;
+  return 256 + size_t(simt_grid(N)) * simt_max_items(W, K, M) * 2048;   // 256-byte header: word [1] = status flags
 }
 
 template <bool GRAD>
@@ -209,7 +209,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) simt_curve_kernel(StepParams p, i
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, lane = tid & 31, warp = tid >> 5;
   const int M = p.M, K = p.K, T = p.T, n_poly = p.n_poly, Kb = p.Kb, X = p.X;
   Smem s = carve(smem_raw, M, W);
-  uint8_t* mask2 = reinterpret_cast<uint8_t*>(p.workspace) + size_t(blockIdx.x) * max_items * 2048;
+  unsigned int* status = reinterpret_cast<unsigned int*>(p.workspace) + 1;   // VLG_STATUS_* flags (header zeroed by the launcher)
+  uint8_t* mask2 = reinterpret_cast<uint8_t*>(p.workspace) + 256 + size_t(blockIdx.x) * max_items * 2048;
+  bool bad_draw = false;
+  if (blockIdx.x == 0 && tid == 0 && !packed_header_ok(p.packed, p.K_total, p.X)) atomicOr(status, unsigned(VLG_STATUS_BAD_PACKED));
   const int WSEG = W - 1;
   const int nwin = (T - 1 + WSEG - 1) / WSEG;
   for (int i = tid; i < 4 * n_poly * Kb; i += NTHREADS) s.basis[i] = p.basis[i];
@@ -254,8 +257,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) simt_curve_kernel(StepParams p, i
           for (int m = 0; m < M; ++m)
             for (int role = 0; role < 2; ++role) {
               uint8_t v = 255;
-              if (pt < nseg)
+              if (pt < nseg) {
                 v = p.draws[(((size_t(n) * p.steps + step) * M + m) * 2 + role) * size_t(T - 1) + seg0 + pt];
+                if (v >= K) { v = uint8_t(K - 1); bad_draw = true; }   // memory safety; reported through the status word
+              }
               s.sel[(m * 2 + role) * W + pt] = v;
             }
         } else {
@@ -524,6 +529,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) simt_curve_kernel(StepParams p, i
     // ---- step epilogue: energy out, penalty gradient, Adam ----
     if (tid == 0) {
       const float E = e_tot / float(M);
+      if (!(fabsf(E) <= 3.0e38f)) atomicOr(status, unsigned(VLG_STATUS_NONFINITE));
       if (p.energy_trace) p.energy_trace[size_t(step) * p.N + n] = E;
       if (step == p.steps - 1) {
         if (p.energy_last) p.energy_last[n] = E;
@@ -555,6 +561,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) simt_curve_kernel(StepParams p, i
   }
   __syncthreads();
   }  // curves of this CTA
+  if (bad_draw) atomicOr(status, unsigned(VLG_STATUS_BAD_DRAW));
 }
 
 cudaError_t launch_simt(const StepParams& p, bool grad, cudaStream_t stream) {
@@ -564,7 +571,8 @@ cudaError_t launch_simt(const StepParams& p, bool grad, cudaStream_t stream) {
   const int grid = simt_grid(p.N);
   const int max_items = simt_max_items(W, p.K, p.M);
   if (p.workspace == nullptr || p.workspace_bytes < simt_workspace_bytes(p.N, p.T, p.K, p.M)) return cudaErrorInvalidValue;
-  cudaError_t e;
+  cudaError_t e = cudaMemsetAsync(p.workspace, 0, 256, stream);
+  if (e != cudaSuccess) return e;
   if (grad) {
     e = cudaFuncSetAttribute(simt_curve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;

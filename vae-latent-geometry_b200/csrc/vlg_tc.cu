@@ -41,6 +41,7 @@
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
+#include "../../include/vlg.h"
 #include "vlg_common.cuh"
 #include "vlg_kernels.h"
 #include "vlg_tcgen05.cuh"
@@ -144,6 +145,13 @@ __device__ __forceinline__ uint32_t relu_tf32(float v) { return __float_as_uint(
 __device__ __forceinline__ void named_bar(int id, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_elect(uint64_t* bar, uint32_t leader) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q mbarrier.arrive.shared::cta.b64 _, [%0];\n\t}" ::"r"(smem_u32(bar)), "r"(leader)
+      : "memory");
+}
 __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -156,7 +164,8 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 
-// work-queue header at the start of the workspace: 64 words + one progress word per curve, 256 B aligned
+// work-queue header at the start of the workspace: 64 words ([0] next unit, [1] status flags VLG_STATUS_*)
+// + one progress word per curve, 256 B aligned
 __host__ __device__ inline size_t tc_queue_words(int N) { return (size_t(64 + N) + 63) / 64 * 64; }
 
 struct WinCtl {
@@ -184,7 +193,8 @@ struct TcSmem {
   unsigned char* ring;  // [chain][stage] 16 KB
   float* XD;            // [m][W][52]: left-end outputs x1, then (after the energy pass) x2 - x1
   uint8_t* sel;         // [m][role][W] drawn decoder per segment
-  uint16_t* rows;       // [K][W] points of the window that drew decoder k
+  uint16_t* rows;       // [K][W] points of the window that drew decoder k, in increasing point order
+  uint16_t* wcnt;       // [K][16] rows of decoder k owned by each epilogue warp (then: exclusive prefix)
   int* cnt;             // [K]
   WinCtl* ctl;          // [2] item lists, double buffered by window parity
   float* sw;            // [chain][SW_SLOTS] 576 floats: W1 (planar), b1, b2, b3 of an item's decoder
@@ -195,13 +205,14 @@ struct TcSmem {
   float* om;            // 56
   float* gacc;          // 20
   float* red;           // 16*20 + 32
-  uint64_t* bars;       // full[2][MAX_STAGES], empty[2][MAX_STAGES], a_ready[2], acc_ready[2], win_ready, sw_full[2][SW_SLOTS]
+  uint64_t* bars;       // full[2][MAX_STAGES], empty[2][MAX_STAGES], a_ready[2], acc_ready[2], win_ready, sw_full[2][SW_SLOTS], ctl_free[2]
   uint32_t* tmem_base;  // [0] TMEM base address, [1] current work unit
 };
 
 constexpr int CTL_FLOATS = (2 * sizeof(WinCtl) + 3) / 4;
 constexpr int SW_SLOTS = 4;            // small-weight buffers per chain (see the producer)
-constexpr int BAR_WORDS = 2 * (4 * MAX_STAGES + 5 + 2 * SW_SLOTS);
+constexpr int BAR_WORDS = 2 * (4 * MAX_STAGES + 5 + 2 * SW_SLOTS + 2);
+static_assert(TC_MAX_M == 2, "the row-list build tests four candidates per point");
 
 // Fixed-size pieces first, at compile-time offsets from the start of dynamic shared memory (their
 // addresses fold into immediates -- the epilogue code is short of registers), then the window-sized
@@ -237,6 +248,7 @@ __device__ __forceinline__ TcSmem tc_carve(unsigned char* base, int W, int K, in
   s.zs = reinterpret_cast<float2*>(f); f += 2 * W;
   s.dzs = reinterpret_cast<float2*>(f); f += 2 * 4 * W;
   s.sel = reinterpret_cast<uint8_t*>(f); f += TC_MAX_M * 2 * W / 4 + 1;
+  s.wcnt = reinterpret_cast<uint16_t*>(f); f += K * 8;
   s.rows = reinterpret_cast<uint16_t*>(f);
   const size_t ring_off = (size_t(reinterpret_cast<unsigned char*>(f) - base) + size_t(K) * W * 2 + 127) / 128 * 128;
   s.ring = base + ring_off;
@@ -248,7 +260,8 @@ __device__ __forceinline__ TcSmem tc_carve(unsigned char* base, int W, int K, in
 
 static size_t tc_smem_fixed_bytes(int W, int K, int M) {
   // everything but the weight rings, in the order of tc_carve (+ alignment slack before the rings)
-  size_t fl = size_t(FIX_FLOATS) + size_t(M) * W * XD_STRIDE + 2 * size_t(W) + 2 * 4 * size_t(W) + TC_MAX_M * 2 * size_t(W) / 4 + 1;
+  size_t fl = size_t(FIX_FLOATS) + size_t(M) * W * XD_STRIDE + 2 * size_t(W) + 2 * 4 * size_t(W) + TC_MAX_M * 2 * size_t(W) / 4 + 1 +
+              size_t(K) * 8;
   return (fl * 4 + size_t(K) * W * 2 + 127) / 128 * 128;
 }
 static int tc_stages(int W, int K, int M) {
@@ -273,6 +286,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
   uint64_t* acc_ready = s.bars + 4 * MAX_STAGES + 2;
   uint64_t* win_ready = s.bars + 4 * MAX_STAGES + 4;
   uint64_t* sw_full = s.bars + 4 * MAX_STAGES + 5;   // [chain][SW_SLOTS]
+  // item list ctl[i] may be rewritten once both producers and both chain states of the issuer are done with it
+  uint64_t* ctl_free = s.bars + 4 * MAX_STAGES + 5 + 2 * SW_SLOTS;   // [2]
   const int nwin = (T - 1 + WSEG - 1) / WSEG;
   // work queue (zeroed by the host before the launch): [0] next unit, [64 + n] chunks done of curve n
   unsigned int* queue = reinterpret_cast<unsigned int*>(p.workspace);
@@ -291,8 +306,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
     mbar_init(&acc_ready[1], 1);
     mbar_init(win_ready, 1);
     for (int i = 0; i < 2 * SW_SLOTS; ++i) mbar_init(&sw_full[i], 1);
+    mbar_init(&ctl_free[0], 4);
+    mbar_init(&ctl_free[1], 4);
     fence_mbar_init();
   }
+  if (blockIdx.x == 0 && tid == 32 && !packed_header_ok(p.packed, p.K_total, p.X))
+    atomicOr(&queue[1], unsigned(VLG_STATUS_BAD_PACKED));
   if (warp == 2) tmem_alloc(s.tmem_base, 512);
   tc_fence_before();
   __syncthreads();
@@ -346,6 +365,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
               }
             }
           }
+        mbar_arrive(&ctl_free[w & 1]);   // done reading this window's item list
       }
     }
   } else if (warp == 2) {
@@ -376,6 +396,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
             if (!mbar_test(win_ready, uint32_t(win[c] & 1))) continue;
             const int nit = s.ctl[win[c] & 1].nitems;
             if (nit < 0) { fin[c] = true; continue; }
+            mbar_arrive_elect(&ctl_free[win[c] & 1], leader);   // the issuer only needs the item count
             nitc[c] = (nit - c + 1) / 2;  // items of this chain in the window
             ops_left[c] = nitc[c] * (GRAD ? 4 : 2);
             opi[c] = 0;
@@ -456,6 +477,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
     const float coefm = 2.0f / float(M);
     long long w_acc = 0;
     long wcount = 0;                            // windows processed by this CTA so far
+    bool bad_draw = false;                      // an explicit draw was >= K (clamped)
     // this CTA's slice of the L2-resident workspace: layer-2 ReLU masks [item][row][4 words], then the
     // right-end decoder outputs x2 [m][W][52].  (The left-end outputs x1 / the differences stay in shared
     // memory: with them in L2 too the dE/dx build sits on L2 latency and the kernel runs 2x slower.)
@@ -523,8 +545,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
               for (int m = 0; m < M; ++m)
                 for (int role = 0; role < 2; ++role) {
                   uint8_t v = 255;
-                  if (pt < nseg)
+                  if (pt < nseg) {
                     v = p.draws[(((size_t(n) * p.steps + step) * M + m) * 2 + role) * size_t(T - 1) + seg0 + pt];
+                    if (v >= K) { v = uint8_t(K - 1); bad_draw = true; }   // memory safety; reported through the status word
+                  }
                   s.sel[(m * 2 + role) * W + pt] = v;
                 }
             } else {
@@ -541,26 +565,60 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
           for (int i = t512; i < 4 * W; i += EPI_THREADS) s.dzs[i] = make_float2(0.f, 0.f);
           if (t512 < K) s.cnt[t512] = 0;
           named_bar(3, EPI_THREADS);
-          // ---- per-decoder row lists ----
-          if (t512 <= nseg) {
+          // ---- per-decoder row lists, in increasing point order ----
+          // Item membership must not depend on thread timing: a decoder drawn by more than 128 points of
+          // the window is split into several items, which run on different chains, and the chains' dz
+          // partial sums are added in a fixed order -- so WHICH points share an item fixes the fp32
+          // summation grouping.  Ordered compaction: thread = point, each warp owns 32 consecutive
+          // points; per decoder a ballot gives the rank inside the warp, a scan over the 16 warps the
+          // warp's base.  (Bit-identical results for any sharding / scheduling of the curves.)
+          {
             const int pt = t512;
-            int cand[2 * TC_MAX_M];
-            int nc = 0;
-            for (int m = 0; m < M; ++m) {
-              if (pt < nseg) cand[nc++] = s.sel[(m * 2 + 0) * W + pt];
-              if (pt >= 1) cand[nc++] = s.sel[(m * 2 + 1) * W + pt - 1];
+            const int wpos = t512 >> 5;            // position of this warp's 32 points in the window
+            int cand[2 * TC_MAX_M], rk[2 * TC_MAX_M];
+#pragma unroll
+            for (int i = 0; i < 2 * TC_MAX_M; ++i) { cand[i] = -1; rk[i] = 0; }
+            if (pt <= nseg) {
+#pragma unroll
+              for (int m = 0; m < TC_MAX_M; ++m)
+                if (m < M) {
+                  if (pt < nseg) cand[2 * m] = s.sel[(m * 2 + 0) * W + pt];
+                  if (pt >= 1) cand[2 * m + 1] = s.sel[(m * 2 + 1) * W + pt - 1];
+                }
+#pragma unroll
+              for (int i = 1; i < 2 * TC_MAX_M; ++i)
+#pragma unroll
+                for (int j = 0; j < i; ++j)
+                  if (cand[j] == cand[i]) cand[i] = -1;   // a point enters a decoder's list once
             }
-            for (int i = 0; i < nc; ++i) {
-              bool dup = false;
-              for (int j = 0; j < i; ++j) dup |= (cand[j] == cand[i]);
-              if (!dup) {
-                const int slot = atomicAdd(&s.cnt[cand[i]], 1);
-                s.rows[cand[i] * W + slot] = uint16_t(pt);
+            const uint32_t lt = (1u << lane) - 1u;
+            for (int k = 0; k < K; ++k) {
+              const bool mem = (cand[0] == k) | (cand[1] == k) | (cand[2] == k) | (cand[3] == k);
+              const uint32_t bal = __ballot_sync(0xffffffffu, mem);
+              const int r = __popc(bal & lt);
+#pragma unroll
+              for (int i = 0; i < 2 * TC_MAX_M; ++i)
+                if (cand[i] == k) rk[i] = r;
+              if (lane == 0) s.wcnt[k * 16 + wpos] = uint16_t(__popc(bal));
+            }
+            named_bar(3, EPI_THREADS);
+            if (t512 < K) {
+              int acc = 0;
+              for (int w = 0; w < 16; ++w) {
+                const int c = s.wcnt[t512 * 16 + w];
+                s.wcnt[t512 * 16 + w] = uint16_t(acc);
+                acc += c;
               }
+              s.cnt[t512] = acc;
             }
+            named_bar(3, EPI_THREADS);
+#pragma unroll
+            for (int i = 0; i < 2 * TC_MAX_M; ++i)
+              if (cand[i] >= 0) s.rows[cand[i] * W + s.wcnt[cand[i] * 16 + wpos] + rk[i]] = uint16_t(pt);
           }
-          named_bar(3, EPI_THREADS);
           if (t512 == 0) {
+            // the control warps must be done with the item list this one replaces (window wcount - 2)
+            if (wcount >= 2) mbar_wait(&ctl_free[wcount & 1], uint32_t(((wcount >> 1) - 1) & 1));
             int ni = 0;
             for (int k = 0; k < K; ++k)
               for (int q = 0; q * 128 < s.cnt[k]; ++q) ctl->item[ni++] = uint16_t(k | (q << 8));
@@ -966,6 +1024,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
         named_bar(3, EPI_THREADS);
         if (t512 == 0) {
           const float E = e_tot / float(M);
+          // fp16 operands overflow above 65504: inf/NaN reach the energy (forward) or omega (backward)
+          if (!(fabsf(E) <= 3.0e38f)) atomicOr(&queue[1], unsigned(VLG_STATUS_NONFINITE));
           if (p.energy_trace) p.energy_trace[size_t(step) * p.N + n] = E;
           if (step == p.steps - 1) {
             if (p.energy_last) p.energy_last[n] = E;
@@ -994,6 +1054,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
         p.omega[size_t(n) * 2 * Kb + t512] = s.om[t512];
         p.adam_m[size_t(n) * 2 * Kb + t512] = s.om[2 * MAX_KB + t512];
         p.adam_v[size_t(n) * 2 * Kb + t512] = s.om[4 * MAX_KB + t512];
+        if (!(fabsf(s.om[t512]) <= 3.0e38f)) atomicOr(&queue[1], unsigned(VLG_STATUS_NONFINITE));
         __threadfence();
       }
       named_bar(3, EPI_THREADS);
@@ -1002,8 +1063,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
         asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&queue[64 + n]), "r"(v) : "memory");
       }
     }  // work units
+    if (bad_draw) atomicOr(&queue[1], unsigned(VLG_STATUS_BAD_DRAW));
     // tell the control warps that there is no more work
     if (t512 == 0) {
+      if (wcount >= 2) mbar_wait(&ctl_free[wcount & 1], uint32_t(((wcount >> 1) - 1) & 1));
       s.ctl[wcount & 1].nitems = -1;
       __threadfence_block();
       mbar_arrive(win_ready);

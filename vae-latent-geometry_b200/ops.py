@@ -59,9 +59,24 @@ def workspace_bytes(N: int, T: int, n_poly: int, K_active: int, M: int, precisio
     return _lib.load().vlg_workspace_bytes(N, T, n_poly, K_active, M, precision)
 
 
+STATUS_BAD_DRAW, STATUS_NONFINITE, STATUS_BAD_PACKED = 1, 2, 4
+
+
+def workspace_status(workspace: torch.Tensor) -> int:
+    """VLG_STATUS_* flags of the last step-kernel launch that used `workspace` (synchronises the stream)."""
+    import ctypes
+    flags = ctypes.c_int(0)
+    with torch.cuda.device(workspace.device):
+        rc = _lib.load().vlg_workspace_status(_chk(workspace, "workspace", dtype=torch.uint8), ctypes.byref(flags),
+                                              _stream(workspace))
+    if rc not in (0, -6):
+        _lib.check(rc, "vlg_workspace_status")
+    return flags.value
+
+
 @torch.library.custom_op("vlg::optimize_steps",
                          mutates_args=("omega", "adam_m", "adam_v", "energy_last", "energy_trace", "workspace"))
-def optimize_steps(packed: torch.Tensor, k_active: int, n_poly: int, M: int, steps: int, step0: int,
+def optimize_steps(packed: torch.Tensor, k_total: int, x_dim: int, k_active: int, n_poly: int, M: int, steps: int, step0: int,
                    a: torch.Tensor, b: torch.Tensor, omega: torch.Tensor, adam_m: torch.Tensor,
                    adam_v: torch.Tensor, basis: torch.Tensor, t: torch.Tensor,
                    draws: Optional[torch.Tensor], seed: int, curve_id0: int, lr: float, beta1: float,
@@ -72,7 +87,7 @@ def optimize_steps(packed: torch.Tensor, k_active: int, n_poly: int, M: int, ste
     T = t.shape[0]
     if Kb != n_poly + 1:
         raise _lib.VlgError(f"omega has Kb={Kb}, expected n_poly+1={n_poly + 1}")
-    args = [_chk(packed, "packed", dtype=packed.dtype), k_active, N, T, n_poly, M, steps, step0,
+    args = [_chk(packed, "packed", dtype=packed.dtype), k_total, x_dim, k_active, N, T, n_poly, M, steps, step0,
             _chk(a, "a", shape=(N, 2)), _chk(b, "b", shape=(N, 2)), _chk(omega, "omega", shape=(N, Kb, 2)),
             _chk(adam_m, "adam_m", shape=(N, Kb, 2)), _chk(adam_v, "adam_v", shape=(N, Kb, 2)),
             _chk(basis, "basis", shape=(4 * n_poly, Kb)), _chk(t, "t", shape=(T,)),
@@ -88,7 +103,7 @@ def optimize_steps(packed: torch.Tensor, k_active: int, n_poly: int, M: int, ste
 
 
 @torch.library.custom_op("vlg::curve_energy", mutates_args=("energy", "length", "workspace"))
-def curve_energy(packed: torch.Tensor, k_active: int, n_poly: int, M: int, a: torch.Tensor,
+def curve_energy(packed: torch.Tensor, k_total: int, x_dim: int, k_active: int, n_poly: int, M: int, a: torch.Tensor,
                  b: torch.Tensor, omega: torch.Tensor, basis: torch.Tensor, t: torch.Tensor,
                  draws: Optional[torch.Tensor], seed: int, curve_id0: int, step: int,
                  energy: torch.Tensor, length: Optional[torch.Tensor], precision: int,
@@ -97,7 +112,7 @@ def curve_energy(packed: torch.Tensor, k_active: int, n_poly: int, M: int, a: to
     T = t.shape[0]
     if Kb != n_poly + 1:
         raise _lib.VlgError(f"omega has Kb={Kb}, expected n_poly+1={n_poly + 1}")
-    args = [_chk(packed, "packed", dtype=packed.dtype), k_active, N, T, n_poly, M,
+    args = [_chk(packed, "packed", dtype=packed.dtype), k_total, x_dim, k_active, N, T, n_poly, M,
             _chk(a, "a", shape=(N, 2)), _chk(b, "b", shape=(N, 2)), _chk(omega, "omega", shape=(N, Kb, 2)),
             _chk(basis, "basis", shape=(4 * n_poly, Kb)), _chk(t, "t", shape=(T,)),
             _chk(draws, "draws", dtype=torch.uint8, shape=(N, 1, M, 2, T - 1)) if draws is not None else 0,
@@ -110,10 +125,12 @@ def curve_energy(packed: torch.Tensor, k_active: int, n_poly: int, M: int, a: to
 
 
 @torch.library.custom_op("vlg::ensemble_std_norm", mutates_args=("out",))
-def ensemble_std_norm(packed: torch.Tensor, k_active: int, grid: torch.Tensor, out: torch.Tensor) -> None:
+def ensemble_std_norm(packed: torch.Tensor, k_total: int, x_dim: int, k_active: int, grid: torch.Tensor,
+                      out: torch.Tensor) -> None:
     G = grid.shape[0]
     with torch.cuda.device(grid.device):
-        _lib.check(_lib.load().vlg_ensemble_std_norm(_chk(packed, "packed", dtype=packed.dtype), k_active, G,
+        _lib.check(_lib.load().vlg_ensemble_std_norm(_chk(packed, "packed", dtype=packed.dtype), k_total, x_dim,
+                                                     k_active, G,
                                                      _chk(grid, "grid", shape=(G, 2)),
                                                      _chk(out, "out", shape=(G,)), _stream(grid)),
                    "vlg_ensemble_std_norm")
