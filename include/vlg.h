@@ -128,6 +128,13 @@ int vlg_optimize_steps(const void* packed, int K, int X, int K_active, int N, in
  * (the reference itself never checks: src/optimize.py:164-168 prints whatever it gets). */
 int vlg_workspace_status(const void* workspace, int* flags, void* stream);
 
+/* Work statistics of the last tensor-core launch that used `workspace` (SYNCHRONISES `stream`):
+ * counters[0] = 128-row decoder items executed (each = the four tcgen05 GEMMs of one decoder on up to 128
+ * selected curve points; forward-only launches run two of them), counters[1] = occupied rows of those items.
+ * Row compaction makes the executed tensor FLOPs smaller than the algorithmic K x T count;
+ * bench.py reports both.  counters is a HOST pointer to two uint64.  Zero for the fp32 kernel. */
+int vlg_workspace_counters(const void* workspace, unsigned long long* counters, void* stream);
+
 /* ---- forward-only evaluation --------------------------------------------------------
  * energy[N]  = compute_energy_mc (src/optimize.py:38-75) for the given omega and draws
  *              (draws: uint8 [N,1,M,2,T-1] or NULL -> counter stream at step `step`).

@@ -47,21 +47,27 @@ def build_grid_graph(grid, k=8):
     return csr_matrix((dists.ravel(), (rows, idx.ravel())), shape=(n, n)), tree
 
 
-def build_entropy_weighted_graph(grid, decoders, k=8, eps=1e-8):
-    """Symmetric kNN graph, edge weight = mean of the end points' normalised ensemble disagreement
-    (src/init_splines_ensemble.py:39-68).  The field itself is the CUDA kernel."""
-    grid_dev = grid.to(decoders.device)
-    ent = vlg_b200.ensemble_std_norm(decoders, grid_dev)
-    ent = ((ent - ent.min()) / (ent.max() - ent.min() + eps)).cpu().numpy().astype(np.float64)
-    grid_np = grid.cpu().numpy()
+def entropy_graph_from_field(grid, field, k=8, eps=1e-8):
+    """Symmetric kNN graph, edge weight = mean of the end points' min-max normalised disagreement
+    (src/init_splines_ensemble.py:53-68).  `field` = || std_k f_k(grid) ||, one value per grid node."""
+    ent = torch.as_tensor(field, dtype=torch.float32).cpu()
+    ent = ((ent - ent.min()) / (ent.max() - ent.min() + eps)).numpy()
+    grid_np = grid.cpu().numpy() if isinstance(grid, torch.Tensor) else grid
     tree, _, idx = _knn(grid_np, k)
     n = len(grid_np)
     rows = np.repeat(np.arange(n), k)
     cols = idx.ravel()
-    w = 0.5 * (ent[rows] + ent[cols])
+    # the reference averages two Python floats taken with .item() from the fp32 field
+    w = 0.5 * (ent[rows].astype(np.float64) + ent[cols].astype(np.float64))
     r2, c2, w2 = np.concatenate([rows, cols]), np.concatenate([cols, rows]), np.concatenate([w, w])
     _, first = np.unique(r2.astype(np.int64) * n + c2, return_index=True)  # an edge may be found from both ends
     return csr_matrix((w2[first], (r2[first], c2[first])), shape=(n, n)), tree
+
+
+def build_entropy_weighted_graph(grid, decoders, k=8, eps=1e-8):
+    """src/init_splines_ensemble.py:39-68; the disagreement field itself is the CUDA kernel
+    (vlg_ensemble_std_norm)."""
+    return entropy_graph_from_field(grid, vlg_b200.ensemble_std_norm(decoders, grid.to(decoders.device)), k, eps)
 
 
 def reconstruct_path(predecessors, start, end):
@@ -75,12 +81,13 @@ def reconstruct_path(predecessors, start, end):
     return path[::-1]
 
 
-def initial_splines(latents, pairs, representatives, graph, tree, grid, basis, n_poly, device):
-    """Shortest path per pair -> least-squares spline fit; returns the spline_data list."""
+def shortest_paths(latents, pairs, graph, tree):
+    """KD-tree snap of both end points + Dijkstra (src/init_splines_ensemble.py:160-170), one Dijkstra per
+    DISTINCT source node instead of one per pair.  -> list of (pair index, node path), in pair order; pairs
+    whose end points snap to the same node, or that are not connected, are skipped like in the reference."""
     starts = tree.query(latents[[p[0] for p in pairs]])[1]
     ends = tree.query(latents[[p[1] for p in pairs]])[1]
-    label = {r["index"]: r["label"] for r in representatives}
-    paths, keep = [], []
+    found = []
     for src in np.unique(starts):
         _, pred = dijkstra(graph, indices=int(src), return_predecessors=True)
         for i in np.nonzero(starts == src)[0]:
@@ -88,16 +95,20 @@ def initial_splines(latents, pairs, representatives, graph, tree, grid, basis, n
                 continue
             path = reconstruct_path(pred, int(src), int(ends[i]))
             if path:
-                paths.append(grid[path])
-                keep.append(i)
-    order = np.argsort(keep)
-    paths, keep = [paths[j] for j in order], [keep[j] for j in order]
-    if not paths:
+                found.append((int(i), path))
+    return sorted(found, key=lambda x: x[0])
+
+
+def initial_splines(latents, pairs, representatives, graph, tree, grid, basis, n_poly, device):
+    """Shortest path per pair -> least-squares spline fit; returns the spline_data list."""
+    found = shortest_paths(latents, pairs, graph, tree)
+    label = {r["index"]: r["label"] for r in representatives}
+    if not found:
         return []
-    a, b, omega = vlg_b200.fit_splines_to_paths(paths, basis, n_poly, device)
+    a, b, omega = vlg_b200.fit_splines_to_paths([grid[path] for _, path in found], basis, n_poly, device)
     a, b, omega = a.cpu(), b.cpu(), omega.cpu()
     out = []
-    for j, i in enumerate(keep):
+    for j, (i, _) in enumerate(found):
         ia, ib = pairs[i]
         out.append(formats.init_spline_dict(a[j], b[j], ia, ib, label[ia], label[ib], n_poly, basis, omega[j]))
     return out

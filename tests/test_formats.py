@@ -1,9 +1,13 @@
 """CPU: the reference's file layouts -- writers produce what the readers (and the reference's
 src/eval.py matrix code) expect."""
 import json
+from pathlib import Path
 
 import numpy as np
 import torch
+
+import vlg_b200  # noqa: F401  (import shim for the hyphenated package directory)
+from vlg_b200 import formats
 
 
 def _blob(n_rep=5):
@@ -94,3 +98,103 @@ def test_grid_graphs_without_gpu():
     _, pred = dijkstra(graph, indices=0, return_predecessors=True)
     path = mod.reconstruct_path(pred, 0, 399)
     assert path[0] == 0 and path[-1] == 399 and 15 <= len(path) <= 40
+
+
+# ---------------------------------------------------------------------------------------------
+# Against files the REFERENCE itself wrote (tests/golden/ref_files/, copied verbatim by
+# tests/golden/make_golden_formats.py) and the matrices its own plot_geodesic_matrix builds from them.
+# ---------------------------------------------------------------------------------------------
+REF_FILES = Path(__file__).resolve().parent / "golden" / "ref_files"
+
+
+def _same_value(x, y):
+    if isinstance(x, torch.Tensor):
+        return isinstance(y, torch.Tensor) and x.dtype == y.dtype and x.shape == y.shape and torch.equal(x, y)
+    return type(x) is type(y) and x == y
+
+
+def _same_blob(b1, b2):
+    assert list(b1.keys()) == list(b2.keys())
+    assert b1["representatives"] == b2["representatives"] and b1["pairs"] == b2["pairs"]
+    assert b1.get("metadata") == b2.get("metadata")
+    assert len(b1["spline_data"]) == len(b2["spline_data"])
+    for d1, d2 in zip(b1["spline_data"], b2["spline_data"]):
+        assert list(d1.keys()) == list(d2.keys())
+        for k in d1:
+            assert _same_value(d1[k], d2[k]), k
+
+
+def test_reference_opt_blob_loads_and_round_trips(tmp_path):
+    ref = formats.load_spline_blob(REF_FILES / "spline_batch_opt_euclidean_10.pt")
+    assert len(ref["spline_data"]) == 45 and ref["metadata"]["steps"] == 1000
+    arr = formats.splines_to_arrays(ref["spline_data"])
+    assert arr["a"].shape == (45, 2) and arr["omega"].shape == (45, 5, 2) and arr["basis"].shape == (16, 5) and arr["n_poly"] == 4
+    # rebuild the file from structure-of-arrays with OUR writers, exactly as src/optimize.py (ours) does
+    init = formats.load_spline_blob(REF_FILES / "spline_batch_init_euclidean_10.pt")
+    spline_data = init["spline_data"]
+    om = torch.stack([d["omega_optimized"] for d in ref["spline_data"]])
+    gl = torch.tensor([d["geodesic_length"] for d in ref["spline_data"]], dtype=torch.float64)
+    eu = [d["euclidean_distance"] for d in ref["spline_data"]]
+    formats.write_back_optimized(spline_data, om, gl, eu)
+    md = ref["metadata"]
+    out = tmp_path / "spline_batch_opt_euclidean_10.pt"
+    formats.save_opt_blob(spline_data, init["representatives"], init["pairs"], md["model_name"], md["init_type"],
+                          md["pair_count"], md["mc_samples"], md["steps"], out)
+    _same_blob(formats.load_spline_blob(out), ref)      # same keys, key order, types, dtypes, values
+
+
+def test_reference_init_blob_round_trips(tmp_path):
+    ref = formats.load_spline_blob(REF_FILES / "spline_batch_init_euclidean_10.pt")
+    sd = [formats.init_spline_dict(d["a"], d["b"], d["a_index"], d["b_index"], d["a_label"], d["b_label"], d["n_poly"],
+                                   d["basis"], d["omega_init"]) for d in ref["spline_data"]]
+    formats.save_init_blob(sd, ref["representatives"], ref["pairs"], tmp_path / "i.pt")
+    _same_blob(formats.load_spline_blob(tmp_path / "i.pt"), ref)
+
+
+def test_distance_matrix_equals_the_references_plot_matrix():
+    ref = formats.load_spline_blob(REF_FILES / "spline_batch_opt_euclidean_10.pt")
+    m = np.load(REF_FILES / "matrices.npz")
+    for len_type in ("geodesic", "euclidean_dist"):
+        mat, labels, skipped = formats.distance_matrix(ref, len_type)
+        assert skipped == 0 and mat.shape == (10, 10)
+        assert np.array_equal(mat, m[len_type]) and [str(x) for x in labels] == list(m["labels"])
+    blob2 = {"spline_data": [dict(d) for d in ref["spline_data"][1:]], "representatives": ref["representatives"]}
+    blob2["spline_data"][0]["a_index"] = -7
+    mat, _, skipped = formats.distance_matrix(blob2, "geodesic")
+    assert skipped == 1 and np.array_equal(mat, m["geodesic_missing"], equal_nan=True) and np.isnan(mat).sum() == 4
+
+
+def test_single_decoder_list_matches_reference_file():
+    ref = torch.load(REF_FILES / "spline_batch_optimized_batched_seed12.pt", map_location="cpu", weights_only=False)
+    arr = formats.splines_to_arrays(ref)
+    recs = formats.single_decoder_records(arr["a"], arr["b"], [d["cluster_pair"] for d in ref], arr["n_poly"], arr["basis"],
+                                          torch.stack([d["omega_init"] for d in ref]),
+                                          torch.stack([d["omega_optimized"] for d in ref]),
+                                          [d["length_geodesic"] for d in ref])
+    assert isinstance(recs, list) and len(recs) == len(ref)
+    for r, d in zip(recs, ref):
+        assert list(r.keys()) == list(d.keys())
+        for k in d:
+            if k == "length_euclidean":      # recomputed: ||a - b|| (optimize_energy_batched.py:121)
+                assert abs(r[k] - d[k]) <= 1e-6 * max(1.0, abs(d[k]))
+            else:
+                assert _same_value(r[k], d[k]), k
+
+
+def test_json_files_are_byte_identical_to_the_references(tmp_path):
+    # pairs JSON (src/select_representative_pairs.py:37-44)
+    reps, pairs = formats.load_pairs(REF_FILES / "selected_pairs_10.json")
+    formats.save_pairs(reps, pairs, tmp_path / "p.json")
+    assert (tmp_path / "p.json").read_text() == (REF_FILES / "selected_pairs_10.json").read_text()
+    # CoV JSON (src/eval.py:139-157): rebuilt from its own raw values through cov_payload
+    ref = json.loads((REF_FILES / "cov_values_alldec_alldec.json").read_text())
+    counts = ref["decoder_counts"]
+    raw = {k: ref["raw_cov_geodesic"][str(k)] for k in counts}
+    payload = formats.cov_payload({k: np.mean(raw[k]) for k in counts}, np.mean(ref["raw_cov_euclidean"]), raw,
+                                  ref["raw_cov_euclidean"], ref["seeds"], counts, ref["num_pairs"])
+    (tmp_path / "c.json").write_text(json.dumps(payload, indent=2))
+    assert (tmp_path / "c.json").read_text() == (REF_FILES / "cov_values_alldec_alldec.json").read_text()
+    # distance-matrix JSON (src/single_decoder/density_batched.py:135-142)
+    d = json.loads((REF_FILES / "geodesic_distances_seed12_p12.json").read_text())
+    formats.save_distance_json(d["seed"], d["cluster_ids"], np.array(d["distance_matrix"]), tmp_path / "d.json")
+    assert (tmp_path / "d.json").read_text() == (REF_FILES / "geodesic_distances_seed12_p12.json").read_text()

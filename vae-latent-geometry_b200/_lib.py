@@ -24,6 +24,7 @@ SIGNATURES = {
     "vlg_pack_decoders": (c_int, [c_void_p] * 6 + [c_int, c_int, c_int, c_void_p, c_void_p]),
     "vlg_workspace_bytes": (c_size_t, [c_int] * 6),
     "vlg_workspace_status": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "vlg_workspace_counters": (c_int, [c_void_p, c_void_p, c_void_p]),
     "vlg_optimize_steps": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,  # packed K X ..step0
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,         # a b omega m v
                                    c_void_p, c_void_p, c_void_p, c_uint64, c_int64,           # basis t draws seed id0

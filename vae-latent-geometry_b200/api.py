@@ -184,12 +184,14 @@ def _raise_on_status(ws: torch.Tensor, what: str) -> None:
 def optimize_splines(model: GeodesicSplineBatch, decoders: DecoderEnsemble, t_vals: torch.Tensor, steps: int,
                      M: int = 2, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
                      penalty_weight: float = 1000.0, draws=None, seed: int = 0, curve_id0: int = 0,
-                     precision: Optional[str] = None, return_trace: bool = False, check: bool = True):
+                     precision: Optional[str] = None, return_trace: bool = False, check: bool = True,
+                     stats: Optional[dict] = None):
     """`steps` iterations of the loop at src/optimize.py:155-162 for every curve of `model`
     (fresh Adam state unless the model already stepped).  Returns the energy evaluated in the
     last step [N] (src/optimize.py:168) and, optionally, the per-step energies [steps,N].
     check=True reads the kernel's status word back after the launch (one stream synchronisation) and
-    raises VlgError on a non-finite result (fp16 operand overflow) instead of returning garbage."""
+    raises VlgError on a non-finite result (fp16 operand overflow) instead of returning garbage.
+    stats: a dict that receives the launch's work counters ('items', 'rows'; tensor-core kernels)."""
     N = model.omega.shape[0]
     T = t_vals.shape[0]
     prec = _resolve_precision(precision, decoders, M)
@@ -207,6 +209,8 @@ def optimize_splines(model: GeodesicSplineBatch, decoders: DecoderEnsemble, t_va
     model.step_count += steps
     if check:
         _raise_on_status(ws, "optimize_splines")
+    if stats is not None:
+        stats["items"], stats["rows"] = ops.workspace_counters(ws)
     return (energy, trace) if return_trace else energy
 
 

@@ -158,6 +158,15 @@ int vlg_workspace_status(const void* workspace, int* flags, void* stream) {
   return word == 0 ? VLG_OK : VLG_ERR_NUMERIC;
 }
 
+int vlg_workspace_counters(const void* workspace, unsigned long long* counters, void* stream) {
+  if (!workspace || !counters) return VLG_ERR_INVALID_ARGUMENT;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemcpyAsync(counters, static_cast<const unsigned int*>(workspace) + 2,
+                                  2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  return e == cudaSuccess ? VLG_OK : cuda_fail(e);
+}
+
 int vlg_curve_energy(const void* packed, int K, int X, int K_active, int N, int T, int n_poly, int M, const float* a,
                      const float* b, const float* omega, const float* basis, const float* t, const uint8_t* draws,
                      uint64_t seed, int64_t curve_id0, int step, float* energy, float* length, int precision,

@@ -208,6 +208,13 @@ __global__ void __launch_bounds__(32) fit_splines_kernel(int N, int Lmax, int n_
     for (int r = 0; r < Kb; ++r)
       for (int c = r; c < Kb; ++c) { A[r][c] = acc[q]; A[c][r] = acc[q]; ++q; }
     for (int r = 0; r < Kb; ++r) { A[r][Kb] = acc[q++]; A[r][Kb + 1] = acc[q++]; }
+    // A path with fewer than Kb interior nodes leaves the normal equations rank deficient (every spline through
+    // the nodes is optimal; the reference's LBFGS from omega = 0 lands near the minimum-norm one).  A ridge of
+    // 1e-10 of the mean diagonal picks that solution and is far below fp32 resolution when the rank is full.
+    double tr = 0.0;
+    for (int r = 0; r < Kb; ++r) tr += A[r][r];
+    const double ridge = 1e-10 * tr / double(Kb) + 1e-300;
+    for (int r = 0; r < Kb; ++r) A[r][r] += ridge;
     for (int c = 0; c < Kb; ++c) {
       int piv = c;
       for (int r = c + 1; r < Kb; ++r) if (fabs(A[r][c]) > fabs(A[piv][c])) piv = r;

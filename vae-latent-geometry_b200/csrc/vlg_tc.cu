@@ -67,8 +67,10 @@ constexpr int GROUP_THREADS = 256;    // one epilogue group (chain)
 constexpr int EPI_THREADS = 512;
 constexpr int FIRST_EPI_WARP = 3;
 constexpr int STAGE_BYTES = 16384;
-constexpr int MAX_STAGES = 4;         // per chain
+constexpr int MAX_STAGES = 5;         // per chain
 constexpr int XD_STRIDE = 52;         // floats per stored decoder output row (X <= 52; 16 B rows)
+constexpr int GT_BYTES = 32768;       // dE/dx operand tile of one item in the workspace: fp16 16 KB (3-term: hi tile + lo tile),
+                                      // tf32 32 KB; canonical no-swizzle K-major image [k-chunk][row][16 B], like the weights
 constexpr int TC_MAX_W = 512;         // curve points per window (runtime W <= this); neighbouring windows share one point
 constexpr int TC_MAX_M = 2;           // MC samples supported by this kernel
 constexpr int TC_MAX_K = 64;          // decoders
@@ -126,10 +128,30 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   const __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&h);
 }
+#ifndef VLG_OPT_CVTRELU
+#define VLG_OPT_CVTRELU 1
+#endif
 __device__ __forceinline__ uint32_t pack_relu_h2(float a, float b) {
+#if VLG_OPT_CVTRELU
+  // one instruction: round-to-nearest convert of both values with the ReLU clamp built in
+  uint32_t r;
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+#else
   const __half2 h = __hmax2(__floats2half2_rn(a, b), __float2half2_rn(0.f));
   return *reinterpret_cast<const uint32_t*>(&h);
+#endif
 }
+// 0xFFFF in every 16-bit half of `w` that holds a positive fp16 value (one HSET2.BM)
+__device__ __forceinline__ uint32_t pos_mask_h2(uint32_t w) {
+  return __hgt2_mask(*reinterpret_cast<const __half2*>(&w), __float2half2_rn(0.f));
+}
+// ReLU-mask word layouts.  MASKH (fp16 single-term kernel only): pair p = elements (2p, 2p+1) of a 32-column
+// tile -> bits p and 16+p, taken straight from the packed fp16 activations (HSET2 + LOP3 per pair instead of
+// 2 x (FSETP + LOP)); expanded in the backward pass to 16-bit lane masks with one IMAD.
+#ifndef VLG_OPT_MASKH
+#define VLG_OPT_MASKH 1
+#endif
 // Backward quantities (dE/dx and the hidden-layer gradients) are scaled by 2^6 before they are rounded to
 // fp16 and unscaled in fp32 when dz is accumulated: gradients of a converged curve are O(1e-2 .. 1e-5)
 // per element, fp16 loses precision below 6e-5.
@@ -168,6 +190,13 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
 // + one progress word per curve, 256 B aligned
 __host__ __device__ inline size_t tc_queue_words(int N) { return (size_t(64 + N) + 63) / 64 * 64; }
 
+// Per-CTA slice of the L2-resident workspace, in 32-bit words: layer-2 ReLU masks [K+16 items][128 rows][4],
+// left-end decoder outputs x1 [M][W][52] and right-end outputs x2 [M][W][52] (fp32), dE/dx operand tiles
+// [K+16 items][GT_BYTES].  (K + 16 >= sum_k ceil(n_k / 128) for W <= 512, M <= 2.)
+__host__ __device__ inline size_t tc_ws_cta_words(int K, int M, int W) {
+  return (size_t(K + 16) * 512 + 2 * size_t(M) * W * XD_STRIDE + size_t(K + 16) * (GT_BYTES / 4) + 31) / 32 * 32;
+}
+
 struct WinCtl {
   int nitems;
   int pad;
@@ -191,7 +220,6 @@ __device__ __forceinline__ void acc_wait(uint64_t* bar, uint32_t parity, int lan
 
 struct TcSmem {
   unsigned char* ring;  // [chain][stage] 16 KB
-  float* XD;            // [m][W][52]: left-end outputs x1, then (after the energy pass) x2 - x1
   uint8_t* sel;         // [m][role][W] drawn decoder per segment
   uint16_t* rows;       // [K][W] points of the window that drew decoder k, in increasing point order
   uint16_t* wcnt;       // [K][16] rows of decoder k owned by each epilogue warp (then: exclusive prefix)
@@ -205,13 +233,13 @@ struct TcSmem {
   float* om;            // 56
   float* gacc;          // 20
   float* red;           // 16*20 + 32
-  uint64_t* bars;       // full[2][MAX_STAGES], empty[2][MAX_STAGES], a_ready[2], acc_ready[2], win_ready, sw_full[2][SW_SLOTS], ctl_free[2]
+  uint64_t* bars;       // full[2][MAX_STAGES], empty[2][MAX_STAGES], a_ready[2], acc_ready[2], win_ready, sw_full[2][SW_SLOTS], ctl_free[2], g_ready
   uint32_t* tmem_base;  // [0] TMEM base address, [1] current work unit
 };
 
 constexpr int CTL_FLOATS = (2 * sizeof(WinCtl) + 3) / 4;
 constexpr int SW_SLOTS = 4;            // small-weight buffers per chain (see the producer)
-constexpr int BAR_WORDS = 2 * (4 * MAX_STAGES + 5 + 2 * SW_SLOTS + 2);
+constexpr int BAR_WORDS = 2 * (4 * MAX_STAGES + 5 + 2 * SW_SLOTS + 3);
 static_assert(TC_MAX_M == 2, "the row-list build tests four candidates per point");
 
 // Fixed-size pieces first, at compile-time offsets from the start of dynamic shared memory (their
@@ -227,7 +255,7 @@ constexpr int FIX_BARS = FIX_RED + 352;                     // BAR_WORDS (8-byte
 constexpr int FIX_TMEM = FIX_BARS + BAR_WORDS;              // 4
 constexpr int FIX_CTL = FIX_TMEM + 4;                       // CTL_FLOATS
 constexpr int FIX_CNT = FIX_CTL + CTL_FLOATS;               // TC_MAX_K
-constexpr int FIX_FLOATS = (FIX_CNT + TC_MAX_K + 3) / 4 * 4;  // XD starts 16-byte aligned
+constexpr int FIX_FLOATS = (FIX_CNT + TC_MAX_K + 3) / 4 * 4;
 static_assert(FIX_BARS % 2 == 0, "mbarriers need 8-byte alignment");
 
 __device__ __forceinline__ TcSmem tc_carve(unsigned char* base, int W, int K, int M, int nst) {
@@ -244,7 +272,6 @@ __device__ __forceinline__ TcSmem tc_carve(unsigned char* base, int W, int K, in
   s.ctl = reinterpret_cast<WinCtl*>(f + FIX_CTL);
   s.cnt = reinterpret_cast<int*>(f + FIX_CNT);
   f += FIX_FLOATS;
-  s.XD = f; f += M * W * XD_STRIDE;
   s.zs = reinterpret_cast<float2*>(f); f += 2 * W;
   s.dzs = reinterpret_cast<float2*>(f); f += 2 * 4 * W;
   s.sel = reinterpret_cast<uint8_t*>(f); f += TC_MAX_M * 2 * W / 4 + 1;
@@ -260,7 +287,7 @@ __device__ __forceinline__ TcSmem tc_carve(unsigned char* base, int W, int K, in
 
 static size_t tc_smem_fixed_bytes(int W, int K, int M) {
   // everything but the weight rings, in the order of tc_carve (+ alignment slack before the rings)
-  size_t fl = size_t(FIX_FLOATS) + size_t(M) * W * XD_STRIDE + 2 * size_t(W) + 2 * 4 * size_t(W) + TC_MAX_M * 2 * size_t(W) / 4 + 1 +
+  size_t fl = size_t(FIX_FLOATS) + 2 * size_t(W) + 2 * 4 * size_t(W) + TC_MAX_M * 2 * size_t(W) / 4 + 1 +
               size_t(K) * 8;
   return (fl * 4 + size_t(K) * W * 2 + 127) / 128 * 128;
 }
@@ -288,6 +315,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
   uint64_t* sw_full = s.bars + 4 * MAX_STAGES + 5;   // [chain][SW_SLOTS]
   // item list ctl[i] may be rewritten once both producers and both chain states of the issuer are done with it
   uint64_t* ctl_free = s.bars + 4 * MAX_STAGES + 5 + 2 * SW_SLOTS;   // [2]
+  // the dE/dx operand tiles of the window are in the workspace (phase = window)
+  uint64_t* g_ready = s.bars + 4 * MAX_STAGES + 5 + 2 * SW_SLOTS + 2;
   const int nwin = (T - 1 + WSEG - 1) / WSEG;
   // work queue (zeroed by the host before the launch): [0] next unit, [64 + n] chunks done of curve n
   unsigned int* queue = reinterpret_cast<unsigned int*>(p.workspace);
@@ -308,6 +337,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
     for (int i = 0; i < 2 * SW_SLOTS; ++i) mbar_init(&sw_full[i], 1);
     mbar_init(&ctl_free[0], 4);
     mbar_init(&ctl_free[1], 4);
+    mbar_init(g_ready, 1);
     fence_mbar_init();
   }
   if (blockIdx.x == 0 && tid == 32 && !packed_header_ok(p.packed, p.K_total, p.X))
@@ -332,11 +362,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
       int slot = 0;
       uint32_t ph = 0;
       unsigned swj = 0;   // stream index of the chain's items (forward and backward items of all windows)
+      // dE/dx operand tiles of this CTA in the workspace (see the epilogue)
+      const unsigned char* gtiles = reinterpret_cast<const unsigned char*>(
+          reinterpret_cast<const uint32_t*>(p.workspace) + tc_queue_words(p.N) + size_t(blockIdx.x) * tc_ws_cta_words(K, M, W) +
+          size_t(K + 16) * 512 + 2 * size_t(M) * W * XD_STRIDE);
       for (long w = 0;; ++w) {
         mbar_wait(win_ready, uint32_t(w & 1));
         const WinCtl* ctl = &s.ctl[w & 1];
         const int nit = ctl->nitems;
         if (nit < 0) break;  // no more work units
+        bool g_seen = false;
         for (int phase = 0; phase < (GRAD ? 2 : 1); ++phase)
           for (int i = c; i < nit; i += 2) {
             const int k = ctl->item[i] & 0xFF;
@@ -355,6 +390,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
               const OpInfo oi = op_info<FMT>(phase * 2 + o);
               const char* src = reinterpret_cast<const char*>(dec_ptr(p.packed, k) + oi.img_off);
               const char* src_lo = reinterpret_cast<const char*>(dec_ptr(p.packed, k) + oi.img_lo);
+              if (phase == 1 && o == 0) {
+                // B3: weight stage(s) interleaved with the stage(s) of the item's dE/dx operand tile, in the order
+                // the issuer consumes them -- fp16: W G | tf32: W0 G0 W1 G1 | 3-term: Whi Ghi Glo Wlo
+                const char* gt = reinterpret_cast<const char*>(gtiles) + size_t(i) * GT_BYTES;
+                const char* seq[4];
+                int nseq;
+                if (!F16) { seq[0] = src; seq[1] = gt; seq[2] = src + STAGE_BYTES; seq[3] = gt + STAGE_BYTES; nseq = 4; }
+                else if (X3) { seq[0] = src; seq[1] = gt; seq[2] = gt + STAGE_BYTES; seq[3] = src_lo; nseq = 4; }
+                else { seq[0] = src; seq[1] = gt; nseq = 2; }
+                for (int st = 0; st < nseq; ++st) {
+                  if (st == 1 && !g_seen) {   // the tiles of this window exist once the epilogue's pass is done
+                    mbar_wait(g_ready, uint32_t(w & 1));
+                    g_seen = true;
+                  }
+                  mbar_wait(&emptyc[slot], ph ^ 1);
+                  mbar_expect_tx(&fullc[slot], STAGE_BYTES);
+                  bulk_g2s(ringc + slot * STAGE_BYTES, seq[st], STAGE_BYTES, &fullc[slot]);
+                  if (++slot == nst) { slot = 0; ph ^= 1; }
+                }
+                continue;
+              }
               // 3-term mode: the stages of the main image, then the stages of the residual image
               for (int st = 0; st < (X3 ? 2 : 1) * oi.nstages; ++st) {
                 const char* from = st < oi.nstages ? src + size_t(st) * STAGE_BYTES : src_lo + size_t(st - oi.nstages) * STAGE_BYTES;
@@ -415,6 +471,43 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
           uint64_t* fullc = full + c * MAX_STAGES;
           uint64_t* emptyc = empty + c * MAX_STAGES;
           const unsigned char* ringc = s.ring + c * nst * STAGE_BYTES;
+          if (optype == 2) {
+            // B3 = dE/dx tile (A, shared memory) x W3 image (B, shared memory); stages as the producer queued them
+            constexpr int NS = (F16 && !X3) ? 2 : 4;
+            uint32_t sb[NS];
+            int sl[NS];
+#pragma unroll
+            for (int i = 0; i < NS; ++i) {
+              sl[i] = slot[c];
+              mbar_wait(&fullc[sl[i]], ph[c]);
+              sb[i] = smem_u32(ringc + sl[i] * STAGE_BYTES);
+              if (++slot[c] == nst) { slot[c] = 0; ph[c] ^= 1; }
+            }
+            tc_fence_after();
+            const uint32_t dcol = chain + oi.d_col;
+            // both images: K-major, 16-byte core-matrix rows, 128 rows per k-chunk (LBO 2048 B, SBO 128 B)
+            if (!F16) {
+#pragma unroll
+              for (int ks = 0; ks < 8; ++ks) {   // K = 8 per MMA: two k-chunks of 4 floats; W0 G0 hold k < 32
+                const uint32_t off = uint32_t(ks & 3) * 4096u;
+                umma_tf32_ss_elect(dcol, umma_smem_desc(sb[(ks >> 2) * 2 + 1] + off, 2048u, 128u),
+                                   umma_smem_desc(sb[(ks >> 2) * 2] + off, 2048u, 128u), idesc, ks ? 1u : 0u, leader);
+              }
+            } else {
+#pragma unroll
+              for (int term = 0; term < (X3 ? 3 : 1); ++term) {
+                // 3-term: Ghi Whi, Glo Whi, Ghi Wlo  (stages: 0 Whi, 1 Ghi, 2 Glo, 3 Wlo)
+                const uint32_t a_s = X3 ? sb[term == 1 ? 2 : 1] : sb[1];
+                const uint32_t b_s = X3 ? sb[term == 2 ? 3 : 0] : sb[0];
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)   // K = 16 per MMA: two k-chunks of 8 halves
+                  umma_f16_ss_elect(dcol, umma_smem_desc(a_s + uint32_t(ks) * 4096u, 2048u, 128u),
+                                    umma_smem_desc(b_s + uint32_t(ks) * 4096u, 2048u, 128u), idesc, (term | ks) ? 1u : 0u, leader);
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < NS; ++i) umma_commit_elect(&emptyc[sl[i]], leader);
+          } else
           for (int st = 0; st < (X3 ? 2 : 1) * oi.nstages; ++st) {
             if (!mbar_test(&fullc[slot[c]], ph[c])) { STAT_T0(); mbar_wait(&fullc[slot[c]], ph[c]); STAT_ADD(w_full); }
             tc_fence_after();
@@ -478,13 +571,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
     long long w_acc = 0;
     long wcount = 0;                            // windows processed by this CTA so far
     bool bad_draw = false;                      // an explicit draw was >= K (clamped)
-    // this CTA's slice of the L2-resident workspace: layer-2 ReLU masks [item][row][4 words], then the
-    // right-end decoder outputs x2 [m][W][52].  (The left-end outputs x1 / the differences stay in shared
-    // memory: with them in L2 too the dE/dx build sits on L2 latency and the kernel runs 2x slower.)
-    const size_t ws_cta = size_t(K + 16) * 512 + size_t(M) * W * XD_STRIDE;  // 32-bit words per CTA
-    uint32_t* maskws = reinterpret_cast<uint32_t*>(p.workspace) + tc_queue_words(p.N) + size_t(blockIdx.x) * ws_cta;
-    float* X1 = s.XD;
-    float* X2 = reinterpret_cast<float*>(maskws + size_t(K + 16) * 512);
+    unsigned long long n_items = 0, n_rows = 0; // executed 128-row items / occupied rows (thread 0; launch statistics)
+    // this CTA's slice of the L2-resident workspace (tc_ws_cta_words): ReLU masks, both end-point outputs of
+    // every segment, and the dE/dx operand tiles one fused pass builds from them for the backward items
+    uint32_t* maskws = reinterpret_cast<uint32_t*>(p.workspace) + tc_queue_words(p.N) + size_t(blockIdx.x) * tc_ws_cta_words(K, M, W);
+    float* X1 = reinterpret_cast<float*>(maskws + size_t(K + 16) * 512);
+    float* X2 = X1 + size_t(M) * W * XD_STRIDE;
+    unsigned char* Gt = reinterpret_cast<unsigned char*>(X2 + size_t(M) * W * XD_STRIDE);
 
     for (int i = t512; i < 4 * n_poly * Kb; i += EPI_THREADS) s.basis[i] = p.basis[i];
 
@@ -623,6 +716,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
             for (int k = 0; k < K; ++k)
               for (int q = 0; q * 128 < s.cnt[k]; ++q) ctl->item[ni++] = uint16_t(k | (q << 8));
             ctl->nitems = ni;
+            n_items += unsigned(ni);
+            for (int k = 0; k < K; ++k) n_rows += unsigned(s.cnt[k]);
             __threadfence_block();
             mbar_arrive(win_ready);
           }
@@ -716,10 +811,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                   const float4 b0 = *reinterpret_cast<const float4*>(sw + OFF_B2 + col0 + 32 * hh + j);
                   const float2 p0 = __fadd2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), make_float2(b0.x, b0.y));
                   const float2 p1 = __fadd2_rn(make_float2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])), make_float2(b0.z, b0.w));
-                  if (p0.x > 0.f) bb |= 1u << j;
-                  if (p0.y > 0.f) bb |= 2u << j;
-                  if (p1.x > 0.f) bb |= 4u << j;
-                  if (p1.y > 0.f) bb |= 8u << j;
+                  if (!(VLG_OPT_MASKH && F16 && !X3)) {
+                    if (p0.x > 0.f) bb |= 1u << j;
+                    if (p0.y > 0.f) bb |= 2u << j;
+                    if (p1.x > 0.f) bb |= 4u << j;
+                    if (p1.y > 0.f) bb |= 8u << j;
+                  }
                   if (X3) {
                     uint32_t a0, a1;
                     pack_hilo_h2(fmaxf(p0.x, 0.f), fmaxf(p0.y, 0.f), a0, vlo[j >> 1]);
@@ -729,6 +826,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                   } else if (F16) {
                     // pairs go to v[0:16] (slots j/2, j/2+1 <= j were consumed already)
                     const uint32_t a0 = pack_relu_h2(p0.x, p0.y), a1 = pack_relu_h2(p1.x, p1.y);
+                    if (VLG_OPT_MASKH) {
+                      bb |= pos_mask_h2(a0) & (0x00010001u << (j >> 1));
+                      bb |= pos_mask_h2(a1) & (0x00010001u << ((j >> 1) + 1));
+                    }
                     v[j >> 1] = a0;
                     v[(j >> 1) + 1] = a1;
                   } else {
@@ -782,36 +883,83 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
           }
           named_bar(3, EPI_THREADS);
 
-          // ======================= x2 - x1 and the energy =======================
+          // ============ x2 - x1: the energy and the dE/dx operand tiles of the backward items ============
           if (GRAD) {
-            // The valid rows of one MC sample are contiguous in both buffers: a flat, fully coalesced pass
-            // over 16-byte pieces (x2 from L2, x1 from shared memory, the difference back in place), four
-            // independent pieces per thread in flight.  The energy is the plain sum of squares, in a fixed
-            // order (deterministic).
+            // One task = (item, row, 8 output columns): G = (2/M) * [ sum over the segments whose RIGHT end is this
+            // (point, decoder) of (x2 - x1)  -  sum over those whose LEFT end it is of (x2 - x1) ], written as one 16-byte
+            // piece of the item's K-major operand tile in the workspace (fp16; 3-term mode: hi and lo tiles; tf32: two
+            // 16-byte pieces of fp32).  The producer then brings a whole tile into shared memory with ONE bulk copy and
+            // B3 runs with its A operand from shared memory: no per-item dE/dx build, no epilogue round trip before B3.
+            // A segment's squared length is counted by the row at its left end (exactly one): the energy, in a fixed order.
             float e = 0.f;
-            const int n4 = nseg * (XD_STRIDE / 4);
-            for (int m = 0; m < M; ++m) {
-              const float4* x2 = reinterpret_cast<const float4*>(X2 + m * W * XD_STRIDE);
-              float4* x1 = reinterpret_cast<float4*>(X1 + m * W * XD_STRIDE);
-              for (int i0 = t512; i0 < n4; i0 += 4 * EPI_THREADS) {
-                float4 v[4];
+            const int ntask = nitems * 1024;
+            const float gsc = F16 ? coefm * F16_GRAD_SCALE : coefm;
+            for (int t0 = t512; t0 < ntask; t0 += EPI_THREADS) {
+              const int it = t0 >> 10, c = (t0 >> 7) & 7, r = t0 & 127;
+              const int k = ctl->item[it] & 0xFF, q0 = (ctl->item[it] >> 8) * 128;
+              if (q0 + r >= s.cnt[k]) continue;
+              const int pt = s.rows[k * W + q0 + r];
+              float g[8];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const int i = i0 + j * EPI_THREADS;
-                  v[j] = i < n4 ? __ldcg(x2 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
+              for (int j = 0; j < 8; ++j) g[j] = 0.f;
+              if (c < 7) {
+                const bool wide = c < 6;   // chunk 6 = columns 48..51 (+ zero padding up to 55)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const int i = i0 + j * EPI_THREADS;
-                  if (i < n4) {
-                    const float4 u = x1[i];
-                    const float4 a = make_float4(v[j].x - u.x, v[j].y - u.y, v[j].z - u.z, v[j].w - u.w);
-                    x1[i] = a;
-                    e = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(a.z, a.z, fmaf(a.w, a.w, e))));
+                for (int m = 0; m < TC_MAX_M; ++m) {
+                  if (m >= M) break;
+                  const bool right = pt >= 1 && s.sel[(m * 2 + 1) * W + pt - 1] == k;
+                  const bool left = s.sel[(m * 2 + 0) * W + pt] == k;
+                  float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, b0 = a0, b1 = a0, c0 = a0, c1 = a0, d0 = a0, d1 = a0;
+                  const size_t offl = size_t(m * W + pt) * XD_STRIDE + 8 * c, offr = offl - XD_STRIDE;   // offr only if pt >= 1
+                  if (right) {
+                    a0 = __ldcg(reinterpret_cast<const float4*>(X2 + offr));
+                    b0 = __ldcg(reinterpret_cast<const float4*>(X1 + offr));
+                    if (wide) {
+                      a1 = __ldcg(reinterpret_cast<const float4*>(X2 + offr + 4));
+                      b1 = __ldcg(reinterpret_cast<const float4*>(X1 + offr + 4));
+                    }
                   }
+                  if (left) {
+                    c0 = __ldcg(reinterpret_cast<const float4*>(X2 + offl));
+                    d0 = __ldcg(reinterpret_cast<const float4*>(X1 + offl));
+                    if (wide) {
+                      c1 = __ldcg(reinterpret_cast<const float4*>(X2 + offl + 4));
+                      d1 = __ldcg(reinterpret_cast<const float4*>(X1 + offl + 4));
+                    }
+                  }
+                  g[0] += a0.x - b0.x; g[1] += a0.y - b0.y; g[2] += a0.z - b0.z; g[3] += a0.w - b0.w;
+                  g[4] += a1.x - b1.x; g[5] += a1.y - b1.y; g[6] += a1.z - b1.z; g[7] += a1.w - b1.w;
+                  const float l0 = c0.x - d0.x, l1 = c0.y - d0.y, l2 = c0.z - d0.z, l3 = c0.w - d0.w;
+                  const float l4 = c1.x - d1.x, l5 = c1.y - d1.y, l6 = c1.z - d1.z, l7 = c1.w - d1.w;
+                  g[0] -= l0; g[1] -= l1; g[2] -= l2; g[3] -= l3; g[4] -= l4; g[5] -= l5; g[6] -= l6; g[7] -= l7;
+                  e = fmaf(l0, l0, fmaf(l1, l1, fmaf(l2, l2, fmaf(l3, l3, e))));
+                  e = fmaf(l4, l4, fmaf(l5, l5, fmaf(l6, l6, fmaf(l7, l7, e))));
                 }
               }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) g[j] *= gsc;
+              unsigned char* tile = Gt + size_t(it) * GT_BYTES;
+              if (F16) {
+                uint4 hi, lo;
+                if (X3) {
+                  pack_hilo_h2(g[0], g[1], hi.x, lo.x); pack_hilo_h2(g[2], g[3], hi.y, lo.y);
+                  pack_hilo_h2(g[4], g[5], hi.z, lo.z); pack_hilo_h2(g[6], g[7], hi.w, lo.w);
+                  *reinterpret_cast<uint4*>(tile + 16384 + (c * 128 + r) * 16) = lo;
+                } else {
+                  hi = make_uint4(pack_h2(g[0], g[1]), pack_h2(g[2], g[3]), pack_h2(g[4], g[5]), pack_h2(g[6], g[7]));
+                }
+                *reinterpret_cast<uint4*>(tile + (c * 128 + r) * 16) = hi;
+              } else {
+                uint4 v0, v1;
+                v0 = make_uint4(tf32_round_bits(__float_as_uint(g[0])), tf32_round_bits(__float_as_uint(g[1])),
+                                tf32_round_bits(__float_as_uint(g[2])), tf32_round_bits(__float_as_uint(g[3])));
+                v1 = make_uint4(tf32_round_bits(__float_as_uint(g[4])), tf32_round_bits(__float_as_uint(g[5])),
+                                tf32_round_bits(__float_as_uint(g[6])), tf32_round_bits(__float_as_uint(g[7])));
+                *reinterpret_cast<uint4*>(tile + ((2 * c) * 128 + r) * 16) = v0;
+                *reinterpret_cast<uint4*>(tile + ((2 * c + 1) * 128 + r) * 16) = v1;
+              }
             }
+            fence_proxy_async_all();   // the tiles are read by the TMA engine (async proxy)
             e = warp_sum(e);
             if (lane == 0) s.red[320 + ew] = e;
           } else {
@@ -836,10 +984,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                 const bool ok = ent < nent && (ent % W) < nseg && sub < NV;
                 float q = 0.f;
                 if (ok) {
-                  float4* d0 = reinterpret_cast<float4*>(X1 + ent * XD_STRIDE) + sub;
-                  const float4 u = *d0;
+                  const float4 u = __ldcg(reinterpret_cast<const float4*>(X1 + ent * XD_STRIDE) + sub);
                   const float4 a = make_float4(v[j].x - u.x, v[j].y - u.y, v[j].z - u.z, v[j].w - u.w);
-                  *d0 = a;
                   q = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(a.z, a.z, a.w * a.w)));
                 }
 #pragma unroll
@@ -851,7 +997,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
             l = warp_sum(l);
             if (lane == 0) { s.red[320 + ew] = e; s.red[336 + ew] = l; }
           }
-          if (GRAD) named_bar(3, EPI_THREADS);  // the differences are read by other threads below
+          if (GRAD) {
+            named_bar(3, EPI_THREADS);            // every tile of the window is written (and fenced for the async proxy)
+            if (t512 == 0) mbar_arrive(g_ready);  // -> the producers may bring them into shared memory
+          }
 
           if (GRAD) {
             // =============================== backward ===============================
@@ -866,54 +1015,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
               ++swj;
               const float2 z = s.zs[pt];
               const float2 zx2 = make_float2(z.x, z.x), zy2 = make_float2(z.y, z.y);
-              // mask words for E-B3 (L2 round trip overlaps the G build and the first MMA)
+              // mask words for E-B3 (the L2 round trip overlaps the first MMA)
               uint2 bits = make_uint2(0u, 0u);
               if (active) bits = *reinterpret_cast<const uint2*>(maskws + (it * 128 + row) * 4 + half * 2);
-              // G = dE/dx_k (this point), columns xc0 .. xc0+31 -> X[xc0 : xc0+32]
-              if (wact) {
-                float g[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) g[j] = 0.f;
-                for (int m = 0; m < (active ? M : 0); ++m) {
-                  if (pt >= 1 && s.sel[(m * 2 + 1) * W + pt - 1] == k) {
-                    const float4* d = reinterpret_cast<const float4*>(X1 + (m * W + pt - 1) * XD_STRIDE + xc0);
-#pragma unroll
-                    for (int q = 0; q < 8; ++q)
-                      if (q < nq) {
-                        const float4 v = d[q];
-                        g[4 * q] += v.x; g[4 * q + 1] += v.y; g[4 * q + 2] += v.z; g[4 * q + 3] += v.w;
-                      }
-                  }
-                  if (s.sel[(m * 2 + 0) * W + pt] == k) {
-                    const float4* d = reinterpret_cast<const float4*>(X1 + (m * W + pt) * XD_STRIDE + xc0);
-#pragma unroll
-                    for (int q = 0; q < 8; ++q)
-                      if (q < nq) {
-                        const float4 v = d[q];
-                        g[4 * q] -= v.x; g[4 * q + 1] -= v.y; g[4 * q + 2] -= v.z; g[4 * q + 3] -= v.w;
-                      }
-                  }
-                }
-                if (F16) {
-                  uint32_t v[16], vl[X3 ? 16 : 1];
-#pragma unroll
-                  for (int j = 0; j < 16; ++j) {
-                    const float g0 = (coefm * F16_GRAD_SCALE) * g[2 * j], g1 = (coefm * F16_GRAD_SCALE) * g[2 * j + 1];
-                    if (X3)
-                      pack_hilo_h2(g0, g1, v[j], vl[j]);
-                    else
-                      v[j] = pack_h2(g0, g1);
-                  }
-                  tmem_st16(colX + half * 16, v);
-                  if (X3) tmem_st16(colX + 64 + half * 16, reinterpret_cast<uint32_t(&)[16]>(vl));
-                } else {
-                  uint32_t v[32];
-#pragma unroll
-                  for (int j = 0; j < 32; ++j) v[j] = tf32_round_bits(__float_as_uint(coefm * g[j]));
-                  tmem_st32(colX + xc0, v);
-                }
-              }
-              tmem_wait_st();
+              // B3 takes its A operand (the dE/dx tile) from shared memory: nothing to build here.  This arrive
+              // only tells the issuer that the chain's accumulator columns are free (all tcgen05.ld of the
+              // previous item are complete in program order).
               tc_fence_before();
               mbar_arrive(&a_ready[chain_id]);
               // dh2 = (G W3) * mask2 -> A4 (Y, in place)
@@ -930,6 +1037,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                     uint32_t vl[X3 ? 16 : 1];
 #pragma unroll
                     for (int j = 0; j < 32; j += 2) {
+                      if (VLG_OPT_MASKH && !X3) {
+                        // bits p, 16+p -> 0xFFFF lane masks (no carries: 1 * 0xFFFF, 0x10000 * 0xFFFF)
+                        const uint32_t lanes = ((mb >> (j >> 1)) & 0x00010001u) * 0xFFFFu;
+                        v[j >> 1] = pack_h2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])) & lanes;
+                        continue;
+                      }
                       const float a0 = ((mb >> j) & 1u) ? __uint_as_float(v[j]) : 0.f;
                       const float a1 = ((mb >> (j + 1)) & 1u) ? __uint_as_float(v[j + 1]) : 0.f;
                       if (X3)
@@ -1064,6 +1177,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
       }
     }  // work units
     if (bad_draw) atomicOr(&queue[1], unsigned(VLG_STATUS_BAD_DRAW));
+    if (t512 == 0) {   // launch statistics for vlg_workspace_counters (words [2..5] of the header)
+      atomicAdd(reinterpret_cast<unsigned long long*>(queue + 2), n_items);
+      atomicAdd(reinterpret_cast<unsigned long long*>(queue + 4), n_rows);
+    }
     // tell the control warps that there is no more work
     if (t512 == 0) {
       if (wcount >= 2) mbar_wait(&ctl_free[wcount & 1], uint32_t(((wcount >> 1) - 1) & 1));
@@ -1103,7 +1220,7 @@ static int tc_window_points(int T, int K, int M) {
     const int nwin = atoi(env);
     if (nwin >= 1) {
       const int w = (segs + nwin - 1) / nwin + 1;
-      if (w >= 2 && w <= TC_MAX_W && tc_stages(w, K, M) >= 2) return w;
+      if (w >= 2 && w <= TC_MAX_W && tc_stages(w, K, M) >= 4) return w;
     }
   }
   int best_w = 0;
@@ -1112,12 +1229,11 @@ static int tc_window_points(int T, int K, int M) {
     const int w = (segs + nwin - 1) / nwin + 1;  // points per window
     if (w > TC_MAX_W) continue;
     const int nst = tc_stages(w, K, M);
-    if (nst >= 2) {
+    if (nst >= 4) {   // B3 of the tf32 / 3-term kernels holds four stages at once
       const double mean = w * p, sd = sqrt(w * p * (1.0 - p)) + 1e-9;
       double items = 0.0;
       for (int q = 0; q * 128 < w; ++q) items += 0.5 * erfc((q * 128 + 0.5 - mean) / (sd * 1.4142135623730951));  // P(n > 128 q)
       double cost = nwin * (K * items + 0.35);  // + per-window fixed cost in item units
-      if (nst == 2) cost *= 1.04;               // a two-stage weight ring cannot hold a whole GEMM's weights
       if (cost < best) { best = cost; best_w = w; }
     }
     if (w <= 128) break;
@@ -1129,7 +1245,7 @@ static int tc_window_points(int T, int K, int M) {
 size_t tc_workspace_bytes(int N, int T, int K, int M) {
   if (M > TC_MAX_M || K > TC_MAX_K) return 0;
   const int W = tc_window_points(T, K, M);
-  return tc_queue_words(N) * 4 + size_t(tc_grid(N)) * (size_t(K + 16) * 2048 + size_t(M) * W * XD_STRIDE * 4);
+  return tc_queue_words(N) * 4 + size_t(tc_grid(N)) * tc_ws_cta_words(K, M, W) * 4;
 }
 
 #ifdef VLG_TC_STATS
@@ -1145,7 +1261,7 @@ cudaError_t launch_tc(const StepParams& p, bool grad, cudaStream_t stream) {
   const int W = tc_window_points(p.T, p.K, p.M);
   if (W < 2) return cudaErrorNotSupported;
   const int nst = tc_stages(W, p.K, p.M);
-  if (nst < 2) return cudaErrorNotSupported;
+  if (nst < 4) return cudaErrorNotSupported;
   if (p.workspace == nullptr || p.workspace_bytes < tc_workspace_bytes(p.N, p.T, p.K, p.M)) return cudaErrorInvalidValue;
   const size_t smem = tc_smem_fixed_bytes(W, p.K, p.M) + size_t(2) * nst * STAGE_BYTES;
   const int grid = tc_grid(p.N);

@@ -32,9 +32,30 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// VLG_OPT_WAITHINT > 0: pass a suspend-time hint (ns) so a waiting thread sleeps in hardware instead of
+// re-issuing try_wait / branch pairs (39 % of the executed warp instructions in the round-1 profile)
+#ifndef VLG_OPT_WAITHINT
+#define VLG_OPT_WAITHINT 0
+#endif
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#if VLG_OPT_WAITHINT > 0
+  while (!mbar_try_wait_hint(bar, parity, VLG_OPT_WAITHINT)) {
+  }
+#else
   while (!mbar_try_wait(bar, parity)) {
   }
+#endif
 }
 
 // ---- 1-D bulk copy global -> shared, completion on an mbarrier (TMA engine) ---------------
@@ -193,6 +214,29 @@ __device__ __forceinline__ void umma_f16_ts_elect(uint32_t d_tmem, uint32_t a_tm
       "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(leader)
       : "memory");
 }
+// Both operands in shared memory (descriptors): D[tmem] (+)= A[smem] * B[smem].
+__device__ __forceinline__ void umma_f16_ss_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                  uint32_t accumulate, uint32_t leader) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_ss_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                   uint32_t accumulate, uint32_t leader) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(leader)
+      : "memory");
+}
+// generic-proxy writes (st.global / st.shared) made visible to the async proxy (TMA reads, tcgen05.mma operand reads)
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit_elect(uint64_t* bar, uint32_t leader) {
   asm volatile(
       "{\n\t.reg .pred q;\n\t"

@@ -123,7 +123,7 @@ def save_distance_json(seed: int, cluster_ids, matrix: np.ndarray, path) -> None
     """geodesic_distances_seed*_p*.json (src/single_decoder/density_batched.py:135-142)."""
     Path(path).parent.mkdir(parents=True, exist_ok=True)
     with open(path, "w") as f:
-        json.dump({"seed": seed, "cluster_ids": list(cluster_ids), "distance_matrix": np.asarray(matrix).tolist()}, f)
+        json.dump({"seed": seed, "cluster_ids": list(cluster_ids), "distance_matrix": np.asarray(matrix).tolist()}, f, indent=2)
 
 
 def cov_payload(avg_cov_geo: dict, avg_cov_euc: float, raw_geo: dict, raw_euc: list, seeds, decoder_counts,

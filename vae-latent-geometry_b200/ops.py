@@ -62,6 +62,16 @@ def workspace_bytes(N: int, T: int, n_poly: int, K_active: int, M: int, precisio
 STATUS_BAD_DRAW, STATUS_NONFINITE, STATUS_BAD_PACKED = 1, 2, 4
 
 
+def workspace_counters(workspace: torch.Tensor):
+    """(items, rows) executed by the last tensor-core launch that used `workspace` (synchronises)."""
+    import ctypes
+    out = (ctypes.c_ulonglong * 2)()
+    with torch.cuda.device(workspace.device):
+        _lib.check(_lib.load().vlg_workspace_counters(_chk(workspace, "workspace", dtype=torch.uint8), out,
+                                                      _stream(workspace)), "vlg_workspace_counters")
+    return int(out[0]), int(out[1])
+
+
 def workspace_status(workspace: torch.Tensor) -> int:
     """VLG_STATUS_* flags of the last step-kernel launch that used `workspace` (synchronises the stream)."""
     import ctypes
