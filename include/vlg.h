@@ -107,6 +107,10 @@ size_t vlg_workspace_bytes(int N, int T, int n_poly, int K_active, int M, int pr
  *               a value >= K_active is clamped and flagged (VLG_STATUS_BAD_DRAW).
  *               NULL -> counter-based Philox4x32-10 stream keyed on
  *               (seed, curve_id0+n, step0+s, m, t): independent of sharding.
+ *   decoder_base NULL, or int32 [N]: curve n uses decoders decoder_base[n] .. decoder_base[n]+K_active-1 of
+ *               `packed` instead of 0 .. K_active-1 -- several weight sets (the ensembles of several training
+ *               seeds, src/eval.py:94-113) packed into one buffer and optimised in ONE launch; draws stay
+ *               relative to the curve's own set.  Out-of-range bases are flagged (VLG_STATUS_BAD_PACKED).
  *   energy_last [N]        energy evaluated in the LAST step (before its update), i.e.
  *               what src/optimize.py:168 turns into geodesic_length = sqrt(energy)
  *   energy_trace NULL or [steps,N]: energy of every step (src/optimize.py:164-165)
@@ -116,7 +120,7 @@ size_t vlg_workspace_bytes(int N, int T, int n_poly, int K_active, int M, int pr
 int vlg_optimize_steps(const void* packed, int K, int X, int K_active, int N, int T, int n_poly, int M,
                        int steps, int step0, const float* a, const float* b, float* omega,
                        float* adam_m, float* adam_v, const float* basis, const float* t,
-                       const uint8_t* draws, uint64_t seed, int64_t curve_id0, double lr,
+                       const uint8_t* draws, const int32_t* decoder_base, uint64_t seed, int64_t curve_id0, double lr,
                        double beta1, double beta2, double eps, double penalty_w,
                        float* energy_last, float* energy_trace, int precision,
                        void* workspace, size_t workspace_bytes, void* stream);
@@ -146,7 +150,7 @@ int vlg_workspace_counters(const void* workspace, unsigned long long* counters, 
  */
 int vlg_curve_energy(const void* packed, int K, int X, int K_active, int N, int T, int n_poly, int M,
                      const float* a, const float* b, const float* omega, const float* basis,
-                     const float* t, const uint8_t* draws, uint64_t seed, int64_t curve_id0,
+                     const float* t, const uint8_t* draws, const int32_t* decoder_base, uint64_t seed, int64_t curve_id0,
                      int step, float* energy, float* length, int precision, void* workspace,
                      size_t workspace_bytes, void* stream);
 

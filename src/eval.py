@@ -1,6 +1,6 @@
 """python -m src.eval -- distance matrix / CoV study (drop-in for the reference's src/eval.py:
-same flags and output files).  `--mode cov` batches all pairs of a (seed, k) into one launch of
-the engine (the reference runs 6300 sequential B=1 optimisations, src/eval.py:90-128)."""
+same flags and output files).  `--mode cov` batches all pairs of ALL seeds of a decoder count k into one
+launch of the engine (the reference runs 6300 sequential B=1 optimisations, src/eval.py:90-128)."""
 from __future__ import annotations
 
 import argparse
@@ -40,6 +40,31 @@ def plot_geodesic_matrix(spline_blob, output_path, len_type="geodesic", seed=Non
     return mat
 
 
+def cov_lengths(state_dicts, za, zb, decoder_counts, steps=300, precision=None, draw_seed=0, device="cuda"):
+    """sqrt(energy) after `steps` Adam steps from omega = 0 for every (seed, pair, k) of the CoV study
+    (src/eval.py:108-128), ONE launch per k: the ensembles of all seeds are packed into one buffer and every
+    curve carries the index of its own weight set (decoder_base), so 6 seeds x 105 pairs x 10 decoder counts are
+    10 launches instead of the reference's 6300 sequential B=1 optimisations.
+    za, zb: [S, N, 2] end points per seed.  Returns {k: array [S, N]}."""
+    S, N = za.shape[0], za.shape[1]
+    per_set = evae.num_decoders(state_dicts[0])
+    decoders = vlg_b200.DecoderEnsemble.from_state_dicts(state_dicts, device, num_decoders=per_set)
+    basis, _ = vlg_b200.construct_nullspace_basis(4, device)
+    t_vals = torch.linspace(0, 1, 2000, device=device)
+    a = za.reshape(S * N, 2).to(device).float().contiguous()
+    b = zb.reshape(S * N, 2).to(device).float().contiguous()
+    base = (torch.arange(S, dtype=torch.int32) * per_set).repeat_interleave(N)
+    geo = {}
+    for k in decoder_counts:
+        model = vlg_b200.GeodesicSplineBatch(a, b, basis, torch.zeros((S * N, basis.shape[1], 2), device=device), 4)
+        # a single decoder is the deterministic energy: 11-bit operands cannot resolve it (the engine then runs the
+        # fp32 kernel; the 3-term mode can stay on the tensor pipe)
+        energy = vlg_b200.optimize_splines(model, decoders, t_vals, steps, M=2, seed=draw_seed, precision=precision,
+                                           decoder_base=base, k_active=k)
+        geo[k] = torch.sqrt(energy).view(S, N).cpu().numpy()
+    return geo
+
+
 def run_cov_analysis(seeds, decoder_counts, pairfile, model_dir, data_path, output_plot, steps=300, precision=None,
                      draw_seed=0):
     """CoV of geodesic lengths across seeds for k = 1..10 decoders (src/eval.py:74-159)."""
@@ -49,22 +74,12 @@ def run_cov_analysis(seeds, decoder_counts, pairfile, model_dir, data_path, outp
     ia = torch.tensor([p[0] for p in pairs], device=device)
     ib = torch.tensor([p[1] for p in pairs], device=device)
     N = len(pairs)
-    basis, _ = vlg_b200.construct_nullspace_basis(4, device)
-    t_vals = torch.linspace(0, 1, 2000, device=device)
-    geo = {k: np.zeros((len(seeds), N)) for k in decoder_counts}
-    euc = np.zeros((len(seeds), N))
-    for si, seed in enumerate(seeds):
-        sd = evae.load_state_dict(f"{model_dir}/model_seed{seed}.pt")
-        with torch.no_grad():
-            za, zb = evae.encoder_mean(sd, data[ia]), evae.encoder_mean(sd, data[ib])
-        euc[si] = (za - zb).norm(dim=1).cpu().numpy()
-        decoders = vlg_b200.DecoderEnsemble.from_state_dict(sd, device)
-        for k in decoder_counts:
-            model = vlg_b200.GeodesicSplineBatch(za, zb, basis, torch.zeros((N, basis.shape[1], 2), device=device), 4)
-            # a single decoder is the deterministic energy: TF32 cannot resolve it, use the fp32 kernel
-            prec = "fp32" if k == 1 else precision
-            energy = vlg_b200.optimize_splines(model, decoders[:k], t_vals, steps, M=2, seed=draw_seed, precision=prec)
-            geo[k][si] = torch.sqrt(energy).cpu().numpy()
+    sds = [evae.load_state_dict(f"{model_dir}/model_seed{seed}.pt") for seed in seeds]
+    with torch.no_grad():   # end points = encoder means of the two cells under each seed's encoder (src/eval.py:102-104)
+        za = torch.stack([evae.encoder_mean(sd, data[ia]) for sd in sds])
+        zb = torch.stack([evae.encoder_mean(sd, data[ib]) for sd in sds])
+    euc = (za - zb).norm(dim=2).cpu().numpy()
+    geo = cov_lengths(sds, za, zb, decoder_counts, steps, precision, draw_seed, device)
     cov_geo = {k: [compute_cov(geo[k][:, i]) for i in range(N)] for k in decoder_counts}
     cov_euc = [compute_cov(euc[:, i]) for i in range(N)]
     payload = formats.cov_payload({k: np.mean(cov_geo[k]) for k in decoder_counts}, np.mean(cov_euc), cov_geo, cov_euc,

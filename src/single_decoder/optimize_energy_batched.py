@@ -1,0 +1,85 @@
+"""python -m src.single_decoder.optimize_energy_batched -- single-decoder geodesic optimisation (drop-in for the
+reference's src/single_decoder/optimize_energy_batched.py:59-131: same flags, same input / output files), on the
+B200 engine.  BASELINE config 2.
+
+Same semantics: deterministic energy sum_t ||x(t+1) - x(t)||^2 with ONE decoder (the VAE decoder's mean head,
+rows 0:50 of its last layer), 500 Adam steps (lr 1e-3) from the file's omega_init, final length = poly-line length
+of the POST-update curve (compute_geodesic_lengths, 42-49), output = a bare list of dicts (108-124).
+Differences a user can see: all splines are optimised in one launch (the reference's batch_size only bounded
+memory); the basis is taken from the spline file instead of being recomputed (the null-space basis is not unique
+across LAPACK builds, SURVEY hard part 7); "omega_init" in the output is the real initial omega (the reference
+aliases it with the optimised one, optimize_energy_batched.py:92); under torchrun the list is sharded over GPUs.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+from pathlib import Path
+
+import torch
+
+import vlg_b200
+from vlg_b200 import formats, sharding
+
+
+def main(seed, pairfile, batch_size=250, steps=500, precision="fp32", artifact_dir="src/artifacts"):
+    pair_tag = Path(pairfile).stem.replace("selected_pairs_", "")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("the engine needs a CUDA (B200) device: there is no CPU fallback")
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=device)
+    art = Path(artifact_dir)
+    spline_path = art / f"spline_batch_seed{seed}_p{pair_tag}.pt"
+    decoder_path = art / f"vae_best_seed{seed}.pth"
+    output_path = art / f"spline_batch_optimized_batched_seed{seed}_p{pair_tag}.pt"
+
+    sd = torch.load(decoder_path, map_location="cpu", weights_only=True)
+    decoder = vlg_b200.DecoderEnsemble.from_single_vae_state_dict(sd, device)
+    spline_data = formats.load_spline_blob(spline_path)["spline_data"]
+    arr = formats.splines_to_arrays(spline_data)
+    N, n_poly = len(spline_data), arr["n_poly"]
+    t_vals = torch.linspace(0, 1, 2000, device=device)
+    lo, hi = sharding.shard_range(N, rank, world)
+    if rank == 0:
+        print(f"Optimizing splines 0 to {N - 1}")
+    model = vlg_b200.GeodesicSplineBatch(arr["a"][lo:hi].to(device), arr["b"][lo:hi].to(device), arr["basis"].to(device),
+                                         arr["omega"][lo:hi].to(device).clone(), n_poly)
+    done = 0
+    while done < steps:                       # the reference prints every 50 steps (optimize_energy_batched.py:103-104)
+        ns = min(50, steps - done)
+        vlg_b200.optimize_single_decoder(model, decoder, t_vals, steps=ns, lr=1e-3, precision=precision)
+        if rank == 0:
+            print(f"Step {done}")
+        done += ns
+    lengths = vlg_b200.compute_geodesic_lengths(model, decoder, t_vals)
+    omega_opt = sharding.gather_results(model.omega, N)
+    lengths = sharding.gather_results(lengths, N)
+    if rank == 0:
+        cluster_pairs = [(d["a_label"], d["b_label"]) for d in spline_data]
+        out = formats.single_decoder_records(arr["a"], arr["b"], cluster_pairs, n_poly, arr["basis"], arr["omega"],
+                                             omega_opt.cpu(), lengths.cpu())
+        output_path.parent.mkdir(parents=True, exist_ok=True)
+        torch.save(out, output_path)
+        print(f"Saved: {output_path}")
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+    return output_path
+
+
+if __name__ == "__main__":
+    parser = argparse.ArgumentParser()
+    parser.add_argument("--seed", type=int, required=True)
+    parser.add_argument("--pairfile", type=str, required=True, help="selected_pairs_*.json")
+    parser.add_argument("--steps", type=int, default=500)
+    parser.add_argument("--precision", type=str, default="fp32", choices=["fp32", "f16x3"],
+                        help="fp32: CUDA-core kernel (default; 11-bit tensor-core operands cannot resolve a single "
+                             "decoder's adjacent-point differences); f16x3: 3-term split on the tensor pipe")
+    parser.add_argument("--artifact-dir", type=str, default="src/artifacts")
+    args = parser.parse_args()
+    main(args.seed, args.pairfile, steps=args.steps, precision=args.precision, artifact_dir=args.artifact_dir)

@@ -50,10 +50,10 @@ def test_sizes_and_argument_errors_without_gpu(built_lib):
     assert lib.vlg_workspace_bytes(45, 2000, 4, 10, 2, 3) == lib.vlg_workspace_bytes(45, 2000, 4, 10, 2, 1) > 0
     # null pointers are rejected before any CUDA call
     rc = lib.vlg_optimize_steps(None, 10, 50, 10, 4, 2000, 4, 2, 1, 0, None, None, None, None, None, None, None, None,
-                                0, 0, 1e-3, 0.9, 0.999, 1e-8, 1000.0, None, None, 0, None, 0, None)
+                                None, 0, 0, 1e-3, 0.9, 0.999, 1e-8, 1000.0, None, None, 0, None, 0, None)
     assert rc == -1
     assert lib.vlg_workspace_status(None, None, None) == -1
-    assert lib.vlg_curve_energy(None, 1, 50, 1, 1, 2, 1, 1, None, None, None, None, None, None, 0, 0, 0, None, None, 0,
+    assert lib.vlg_curve_energy(None, 1, 50, 1, 1, 2, 1, 1, None, None, None, None, None, None, None, 0, 0, 0, None, None, 0,
                                 None, 0, None) == -1
 
 

@@ -198,3 +198,25 @@ def test_json_files_are_byte_identical_to_the_references(tmp_path):
     d = json.loads((REF_FILES / "geodesic_distances_seed12_p12.json").read_text())
     formats.save_distance_json(d["seed"], d["cluster_ids"], np.array(d["distance_matrix"]), tmp_path / "d.json")
     assert (tmp_path / "d.json").read_text() == (REF_FILES / "geodesic_distances_seed12_p12.json").read_text()
+
+
+def test_single_decoder_distance_matrix_from_reference_records(tmp_path):
+    """src/single_decoder/density_batched.py (ours) on the reference's committed 45-record single-decoder file:
+    points numbered by first appearance, labels from cluster_pair, symmetric, zero diagonal, every entry a
+    committed length_geodesic; the JSON carries exactly the reference's keys."""
+    import shutil
+    from src.single_decoder import density_batched as db
+    recs = torch.load(REF_FILES / "spline_batch_optimized_batched_seed12.pt", map_location="cpu", weights_only=False)
+    ids, mat = db.distance_matrix_from_records(recs)
+    assert len(ids) == 10 and mat.shape == (10, 10) and not np.isnan(mat).any()
+    assert np.array_equal(mat, mat.T) and (np.diag(mat) == 0).all()
+    assert ids[0] == recs[0]["cluster_pair"][0] and ids[1] == recs[0]["cluster_pair"][1]
+    assert mat[0, 1] == recs[0]["length_geodesic"]
+    assert sorted(mat[np.triu_indices(10, 1)].tolist()) == sorted(r["length_geodesic"] for r in recs)
+    art = tmp_path / "artifacts"
+    art.mkdir()
+    shutil.copyfile(REF_FILES / "spline_batch_optimized_batched_seed12.pt", art / "spline_batch_optimized_batched_seed12_p10.pt")
+    out = db.main(12, "src/artifacts/selected_pairs_10.json", artifact_dir=str(art))
+    d = json.loads(Path(out).read_text())
+    assert list(d.keys()) == ["seed", "cluster_ids", "distance_matrix"] and d["seed"] == 12 and d["cluster_ids"] == ids
+    assert np.array_equal(np.array(d["distance_matrix"]), mat)

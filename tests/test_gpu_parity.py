@@ -274,7 +274,7 @@ def test_kernel_status_word_reports_bad_draws_and_overflow(vlg, prec):
         ws = api._workspace(m, dec_, T, M, code)
         e = torch.empty(N, device="cuda")
         ops.optimize_steps(dec_.packed, dec_.K, dec_.X, len(dec_), 4, M, 1, 0, m.a, m.b, m.omega, m.adam_m, m.adam_v,
-                           m.basis, t, draws, 0, 0, 1e-3, 0.9, 0.999, 1e-8, 1000.0, e, None, code, ws)
+                           m.basis, t, draws, None, 0, 0, 1e-3, 0.9, 0.999, 1e-8, 1000.0, e, None, code, ws)
         return ops.workspace_status(ws), e
 
     assert launch(dec, None)[0] == 0
@@ -584,7 +584,7 @@ def test_kernels_write_only_inside_their_buffers(vlg, prec, T, N, K, M, n_poly):
     b = torch.tensor(rng.uniform(-3, 3, (N, 2)), dtype=torch.float32, device=dev)
     t = torch.linspace(0, 1, T, device=dev)
     ops.optimize_steps(dec.packed, dec.K, dec.X, K, n_poly, M, S, 0, a, b, om.view(N, Kb, 2), m_.view(N, Kb, 2), v_.view(N, Kb, 2),
-                       basis.to(dev).float().contiguous(), t, None, 3, 11, 1e-3, 0.9, 0.999, 1e-8, 1000.0, e_, tr.view(S, N), code,
+                       basis.to(dev).float().contiguous(), t, None, None, 3, 11, 1e-3, 0.9, 0.999, 1e-8, 1000.0, e_, tr.view(S, N), code,
                        ws if nws else None)
     torch.cuda.synchronize()
     for name, buf, (lo, hi) in (("omega", om_buf, om_rng), ("adam_m", m_buf, m_rng), ("adam_v", v_buf, v_rng),

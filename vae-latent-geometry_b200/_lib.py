@@ -27,11 +27,11 @@ SIGNATURES = {
     "vlg_workspace_counters": (c_int, [c_void_p, c_void_p, c_void_p]),
     "vlg_optimize_steps": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,  # packed K X ..step0
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,         # a b omega m v
-                                   c_void_p, c_void_p, c_void_p, c_uint64, c_int64,           # basis t draws seed id0
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_uint64, c_int64,  # basis t draws dec_base seed id0
                                    c_double, c_double, c_double, c_double, c_double,          # lr b1 b2 eps pen
                                    c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
     "vlg_curve_energy": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
-                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_uint64, c_int64, c_int, c_void_p, c_void_p, c_int, c_void_p,
                                  c_size_t, c_void_p]),
     "vlg_ensemble_std_norm": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),

@@ -68,6 +68,19 @@ class DecoderEnsemble:
                                grab(4, "weight"), grab(4, "bias"), device)
 
     @classmethod
+    def from_state_dicts(cls, state_dicts, device, num_decoders: Optional[int] = None) -> "DecoderEnsemble":
+        """Several EVAE checkpoints (e.g. the six seeds of the CoV study) packed back to back into ONE buffer:
+        set s occupies decoders s * K .. s * K + K - 1; use with optimize_splines(decoder_base=..., k_active=...)."""
+        parts = []
+        for sd in state_dicts:
+            if num_decoders is None:
+                ids = {int(k.split(".")[1]) for k in sd if k.startswith("decoder.") and k.split(".")[1].isdigit()}
+                num_decoders = max(ids) + 1
+            parts.append([torch.stack([sd[f"decoder.{i}.decoder_net.{l}.{w}"].float() for i in range(num_decoders)])
+                          for l, w in ((0, "weight"), (0, "bias"), (2, "weight"), (2, "bias"), (4, "weight"), (4, "bias"))])
+        return cls.from_arrays(*[torch.cat([p[j] for p in parts]) for j in range(6)], device)
+
+    @classmethod
     def from_single_vae_state_dict(cls, state_dict, device, out_dim: int = 50) -> "DecoderEnsemble":
         """Single VAE (src/artifacts/vae_best_seed*.pth): the decoder's last layer emits
         mean || log_std; ``.mean`` is rows 0:out_dim (src/single_decoder/vae.py:29-42)."""
@@ -185,17 +198,28 @@ def optimize_splines(model: GeodesicSplineBatch, decoders: DecoderEnsemble, t_va
                      M: int = 2, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
                      penalty_weight: float = 1000.0, draws=None, seed: int = 0, curve_id0: int = 0,
                      precision: Optional[str] = None, return_trace: bool = False, check: bool = True,
-                     stats: Optional[dict] = None):
+                     stats: Optional[dict] = None, decoder_base=None, k_active: Optional[int] = None):
     """`steps` iterations of the loop at src/optimize.py:155-162 for every curve of `model`
     (fresh Adam state unless the model already stepped).  Returns the energy evaluated in the
     last step [N] (src/optimize.py:168) and, optionally, the per-step energies [steps,N].
     check=True reads the kernel's status word back after the launch (one stream synchronisation) and
     raises VlgError on a non-finite result (fp16 operand overflow) instead of returning garbage.
-    stats: a dict that receives the launch's work counters ('items', 'rows'; tensor-core kernels)."""
+    stats: a dict that receives the launch's work counters ('items', 'rows'; tensor-core kernels).
+    decoder_base / k_active: several weight sets in one launch -- curve n uses decoders
+    decoder_base[n] .. decoder_base[n] + k_active - 1 of `decoders` (e.g. the ensembles of several training
+    seeds packed with DecoderEnsemble.from_state_dicts; the CoV study of src/eval.py:90-128 in 10 launches)."""
     N = model.omega.shape[0]
     T = t_vals.shape[0]
-    prec = _resolve_precision(precision, decoders, M)
     dev = model.omega.device
+    if decoder_base is not None:
+        if k_active is None:
+            raise _lib.VlgError("decoder_base needs k_active (decoders per weight set)")
+        decoder_base = torch.as_tensor(decoder_base)
+        if tuple(decoder_base.shape) != (N,) or int(decoder_base.min()) < 0 or int(decoder_base.max()) + k_active > decoders.K:
+            raise _lib.VlgError(f"decoder_base must be [N] with 0 <= base and base + {k_active} <= {decoders.K}")
+        decoder_base = decoder_base.to(device=dev, dtype=torch.int32).contiguous()
+        decoders = DecoderEnsemble(decoders.packed, decoders.K, decoders.X, k_active=k_active)
+    prec = _resolve_precision(precision, decoders, M)
     energy = torch.empty(N, dtype=torch.float32, device=dev)
     trace = torch.empty((steps, N), dtype=torch.float32, device=dev) if return_trace else None
     if steps <= 0:
@@ -204,7 +228,7 @@ def optimize_splines(model: GeodesicSplineBatch, decoders: DecoderEnsemble, t_va
     ops.optimize_steps(decoders.packed, decoders.K, decoders.X, len(decoders), model.n_poly, M, steps,
                        model.step_count, model.a, model.b,
                        model.omega, model.adam_m, model.adam_v, model.basis, t_vals.contiguous().float(),
-                       _prep_draws(draws, N, steps, M, T, dev, len(decoders)), seed, curve_id0, lr, betas[0],
+                       _prep_draws(draws, N, steps, M, T, dev, len(decoders)), decoder_base, seed, curve_id0, lr, betas[0],
                        betas[1], eps, penalty_weight, energy, trace, prec, ws)
     model.step_count += steps
     if check:
@@ -227,7 +251,7 @@ def compute_energy_mc(model: GeodesicSplineBatch, decoders: DecoderEnsemble, t_v
     ws = _workspace(model, decoders, T, M, prec)
     ops.curve_energy(decoders.packed, decoders.K, decoders.X, len(decoders), model.n_poly, M, model.a, model.b,
                      model.omega, model.basis, t_vals.contiguous().float(),
-                     _prep_draws(draws, N, 1, M, T, dev, len(decoders)), seed, curve_id0, step,
+                     _prep_draws(draws, N, 1, M, T, dev, len(decoders)), None, seed, curve_id0, step,
                      energy, length, prec, ws)
     if check:
         _raise_on_status(ws, "compute_energy_mc")

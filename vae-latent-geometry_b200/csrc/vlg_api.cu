@@ -105,8 +105,8 @@ size_t vlg_workspace_bytes(int N, int T, int n_poly, int K_active, int M, int pr
 
 int vlg_optimize_steps(const void* packed, int K, int X, int K_active, int N, int T, int n_poly, int M, int steps, int step0,
                        const float* a, const float* b, float* omega, float* adam_m, float* adam_v,
-                       const float* basis, const float* t, const uint8_t* draws, uint64_t seed, int64_t curve_id0,
-                       double lr, double beta1, double beta2, double eps, double penalty_w, float* energy_last,
+                       const float* basis, const float* t, const uint8_t* draws, const int32_t* decoder_base, uint64_t seed,
+                       int64_t curve_id0, double lr, double beta1, double beta2, double eps, double penalty_w, float* energy_last,
                        float* energy_trace, int precision, void* workspace, size_t workspace_bytes, void* stream) {
   if (!a || !b || !omega || !adam_m || !adam_v || !basis || !t || steps < 0 || step0 < 0)
     return VLG_ERR_INVALID_ARGUMENT;
@@ -128,6 +128,7 @@ int vlg_optimize_steps(const void* packed, int K, int X, int K_active, int N, in
   p.basis = basis;
   p.t = t;
   p.draws = draws;
+  p.dec_base = decoder_base;
   p.seed = seed;
   p.curve_id0 = curve_id0;
   p.lr = lr;
@@ -169,7 +170,7 @@ int vlg_workspace_counters(const void* workspace, unsigned long long* counters, 
 
 int vlg_curve_energy(const void* packed, int K, int X, int K_active, int N, int T, int n_poly, int M, const float* a,
                      const float* b, const float* omega, const float* basis, const float* t, const uint8_t* draws,
-                     uint64_t seed, int64_t curve_id0, int step, float* energy, float* length, int precision,
+                     const int32_t* decoder_base, uint64_t seed, int64_t curve_id0, int step, float* energy, float* length, int precision,
                      void* workspace, size_t workspace_bytes, void* stream) {
   if (!a || !b || !omega || !basis || !t || !energy || step < 0) return VLG_ERR_INVALID_ARGUMENT;
   int rc = check_device();
@@ -187,6 +188,7 @@ int vlg_curve_energy(const void* packed, int K, int X, int K_active, int N, int 
   p.basis = basis;
   p.t = t;
   p.draws = draws;
+  p.dec_base = decoder_base;
   p.seed = seed;
   p.curve_id0 = curve_id0;
   p.energy_last = energy;

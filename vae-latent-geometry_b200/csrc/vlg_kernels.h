@@ -23,6 +23,7 @@ struct StepParams {
   const float* basis;
   const float* t;
   const uint8_t* draws;        // [N][steps][M][2][T-1] or null
+  const int32_t* dec_base;     // [N] or null: curve n uses decoders dec_base[n] .. dec_base[n] + K - 1 of `packed`
   uint64_t seed;
   int64_t curve_id0;
   double lr, beta1, beta2;

@@ -228,6 +228,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) simt_curve_kernel(StepParams p, i
   }
   const float2 pa = make_float2(p.a[2 * n], p.a[2 * n + 1]);
   const float2 pb = make_float2(p.b[2 * n], p.b[2 * n + 1]);
+  int dec_base = p.dec_base ? p.dec_base[n] : 0;   // first decoder of this curve's weight set inside `packed`
+  if (dec_base < 0 || dec_base + K > p.K_total) {
+    dec_base = 0;
+    if (tid == 0) atomicOr(status, unsigned(VLG_STATUS_BAD_PACKED));
+  }
   const float coefm = 2.0f / float(M);
   __syncthreads();
 
@@ -312,7 +317,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) simt_curve_kernel(StepParams p, i
         const int k = s.item[it] & 0xFF, q0 = (s.item[it] >> 8) * 128;
         const int nrows = min(128, s.cnt[k] - q0);
         const uint16_t* rl = s.rows + k * W + q0;
-        const float* dec = dec_ptr(p.packed, k);
+        const float* dec = dec_ptr(p.packed, dec_base + k);
         for (int i = tid; i < 576; i += NTHREADS) s.sw[i] = __ldg(dec + i);
         __syncthreads();
         {  // layer 1 on CUDA cores -> As[c][row]
@@ -421,7 +426,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) simt_curve_kernel(StepParams p, i
           const int k = s.item[it] & 0xFF, q0 = (s.item[it] >> 8) * 128;
           const int nrows = min(128, s.cnt[k] - q0);
           const uint16_t* rl = s.rows + k * W + q0;
-          const float* dec = dec_ptr(p.packed, k);
+          const float* dec = dec_ptr(p.packed, dec_base + k);
           for (int i = tid; i < 576; i += NTHREADS) s.sw[i] = __ldg(dec + i);
           {  // G = dE/dx_k  -> As[c][row], c < 64
             const int row = tid & 127, c0 = (tid >> 7) * 32;

@@ -41,6 +41,8 @@
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "../../include/vlg.h"
 #include "vlg_common.cuh"
 #include "vlg_kernels.h"
@@ -199,7 +201,7 @@ __host__ __device__ inline size_t tc_ws_cta_words(int K, int M, int W) {
 
 struct WinCtl {
   int nitems;
-  int pad;
+  int base;      // first decoder of the curve's weight set inside `packed` (StepParams::dec_base)
   uint16_t item[MAX_ITEMS];  // decoder | pass << 8
 };
 
@@ -225,6 +227,7 @@ struct TcSmem {
   uint16_t* wcnt;       // [K][16] rows of decoder k owned by each epilogue warp (then: exclusive prefix)
   int* cnt;             // [K]
   WinCtl* ctl;          // [2] item lists, double buffered by window parity
+  float* XD;            // [m][W][52] left-end outputs x1, then x2 - x1 (only when they fit: xl2 == 0; else in the workspace)
   float* sw;            // [chain][SW_SLOTS] 576 floats: W1 (planar), b1, b2, b3 of an item's decoder
   float2* zs;           // W latent points of the window
   float2* dzs;          // [chain][half][W]
@@ -255,10 +258,10 @@ constexpr int FIX_BARS = FIX_RED + 352;                     // BAR_WORDS (8-byte
 constexpr int FIX_TMEM = FIX_BARS + BAR_WORDS;              // 4
 constexpr int FIX_CTL = FIX_TMEM + 4;                       // CTL_FLOATS
 constexpr int FIX_CNT = FIX_CTL + CTL_FLOATS;               // TC_MAX_K
-constexpr int FIX_FLOATS = (FIX_CNT + TC_MAX_K + 3) / 4 * 4;
+constexpr int FIX_FLOATS = (FIX_CNT + TC_MAX_K + 3) / 4 * 4;  // XD starts 16-byte aligned
 static_assert(FIX_BARS % 2 == 0, "mbarriers need 8-byte alignment");
 
-__device__ __forceinline__ TcSmem tc_carve(unsigned char* base, int W, int K, int M, int nst) {
+__device__ __forceinline__ TcSmem tc_carve(unsigned char* base, int W, int K, int M, int xl2) {
   TcSmem s;
   float* f = reinterpret_cast<float*>(base);
   s.sw = f + FIX_SW;
@@ -272,6 +275,7 @@ __device__ __forceinline__ TcSmem tc_carve(unsigned char* base, int W, int K, in
   s.ctl = reinterpret_cast<WinCtl*>(f + FIX_CTL);
   s.cnt = reinterpret_cast<int*>(f + FIX_CNT);
   f += FIX_FLOATS;
+  s.XD = f; f += xl2 ? 0 : M * W * XD_STRIDE;
   s.zs = reinterpret_cast<float2*>(f); f += 2 * W;
   s.dzs = reinterpret_cast<float2*>(f); f += 2 * 4 * W;
   s.sel = reinterpret_cast<uint8_t*>(f); f += TC_MAX_M * 2 * W / 4 + 1;
@@ -279,33 +283,33 @@ __device__ __forceinline__ TcSmem tc_carve(unsigned char* base, int W, int K, in
   s.rows = reinterpret_cast<uint16_t*>(f);
   const size_t ring_off = (size_t(reinterpret_cast<unsigned char*>(f) - base) + size_t(K) * W * 2 + 127) / 128 * 128;
   s.ring = base + ring_off;
-  (void)nst;
   return s;
 }
 
 }  // namespace
 
-static size_t tc_smem_fixed_bytes(int W, int K, int M) {
+static size_t tc_smem_fixed_bytes(int W, int K, int M, int xl2) {
   // everything but the weight rings, in the order of tc_carve (+ alignment slack before the rings)
-  size_t fl = size_t(FIX_FLOATS) + 2 * size_t(W) + 2 * 4 * size_t(W) + TC_MAX_M * 2 * size_t(W) / 4 + 1 +
+  size_t fl = size_t(FIX_FLOATS) + (xl2 ? 0 : size_t(M) * W * XD_STRIDE) + 2 * size_t(W) + 2 * 4 * size_t(W) + TC_MAX_M * 2 * size_t(W) / 4 + 1 +
               size_t(K) * 8;
   return (fl * 4 + size_t(K) * W * 2 + 127) / 128 * 128;
 }
-static int tc_stages(int W, int K, int M) {
-  const long budget = 232448 - long(tc_smem_fixed_bytes(W, K, M));
+static int tc_stages(int W, int K, int M, int xl2) {
+  const long budget = 232448 - long(tc_smem_fixed_bytes(W, K, M, xl2));
   long nst = budget / (2 * STAGE_BYTES);
   if (nst > MAX_STAGES) nst = MAX_STAGES;
   return int(nst);
 }
 
-template <bool GRAD, int FMT>
+template <bool GRAD, int FMT, bool XL2>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, int nst, int W) {
+  constexpr bool xl2 = XL2;               // left-end outputs / differences in the L2 workspace instead of shared memory
   constexpr bool F16 = FMT != FMT_TF32;   // fp16 operands (one or two terms)
   constexpr bool X3 = FMT == FMT_F16X3;   // 3-term split
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int M = p.M, K = p.K, T = p.T, n_poly = p.n_poly, Kb = p.Kb;
-  TcSmem s = tc_carve(smem_raw, W, K, M, nst);
+  TcSmem s = tc_carve(smem_raw, W, K, M, xl2);
   const int WSEG = W - 1;  // segments per window
   uint64_t* full = s.bars;                       // [2][MAX_STAGES]
   uint64_t* empty = s.bars + 2 * MAX_STAGES;     // [2][MAX_STAGES]
@@ -374,7 +378,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
         bool g_seen = false;
         for (int phase = 0; phase < (GRAD ? 2 : 1); ++phase)
           for (int i = c; i < nit; i += 2) {
-            const int k = ctl->item[i] & 0xFF;
+            const int k = ctl->base + (ctl->item[i] & 0xFF);
             // Small weights of this item into slot swj % SW_SLOTS.  No "slot free" barrier is needed: the
             // producer is here only after it issued every weight stage of the previous item, the last of
             // which went into a ring slot that an MMA of item j-1 or j-2 had released (the ring holds at
@@ -390,23 +394,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
               const OpInfo oi = op_info<FMT>(phase * 2 + o);
               const char* src = reinterpret_cast<const char*>(dec_ptr(p.packed, k) + oi.img_off);
               const char* src_lo = reinterpret_cast<const char*>(dec_ptr(p.packed, k) + oi.img_lo);
-              if (phase == 1 && o == 0) {
-                // B3: weight stage(s) interleaved with the stage(s) of the item's dE/dx operand tile, in the order
-                // the issuer consumes them -- fp16: W G | tf32: W0 G0 W1 G1 | 3-term: Whi Ghi Glo Wlo
+              if (xl2 && phase == 1 && o == 0) {
+                // B3: (weight stage, dE/dx tile stage) pairs in the order the issuer consumes them.  fp16: one pair,
+                // the whole contraction (k < 64).  tf32 and 3-term: two pairs, one per half of the contraction
+                // (tf32: 16 KB of each image per half; 3-term: hi half | lo half, 8 KB each, in one stage) -- so
+                // no more than two stages are live at a time and a two-stage ring is enough.
                 const char* gt = reinterpret_cast<const char*>(gtiles) + size_t(i) * GT_BYTES;
-                const char* seq[4];
-                int nseq;
-                if (!F16) { seq[0] = src; seq[1] = gt; seq[2] = src + STAGE_BYTES; seq[3] = gt + STAGE_BYTES; nseq = 4; }
-                else if (X3) { seq[0] = src; seq[1] = gt; seq[2] = gt + STAGE_BYTES; seq[3] = src_lo; nseq = 4; }
-                else { seq[0] = src; seq[1] = gt; nseq = 2; }
-                for (int st = 0; st < nseq; ++st) {
-                  if (st == 1 && !g_seen) {   // the tiles of this window exist once the epilogue's pass is done
+                constexpr int NPAIR = (F16 && !X3) ? 1 : 2;
+                for (int st = 0; st < 2 * NPAIR; ++st) {
+                  const int kh = st >> 1;
+                  const bool is_g = st & 1;
+                  if (is_g && !g_seen) {   // the tiles of this window exist once the epilogue's pass is done
                     mbar_wait(g_ready, uint32_t(w & 1));
                     g_seen = true;
                   }
                   mbar_wait(&emptyc[slot], ph ^ 1);
                   mbar_expect_tx(&fullc[slot], STAGE_BYTES);
-                  bulk_g2s(ringc + slot * STAGE_BYTES, seq[st], STAGE_BYTES, &fullc[slot]);
+                  unsigned char* dst = ringc + slot * STAGE_BYTES;
+                  if (X3) {
+                    const char* hi = is_g ? gt : src;
+                    const char* lo = is_g ? gt + 16384 : src_lo;
+                    bulk_g2s(dst, hi + kh * 8192, 8192, &fullc[slot]);
+                    bulk_g2s(dst + 8192, lo + kh * 8192, 8192, &fullc[slot]);
+                  } else {
+                    bulk_g2s(dst, (is_g ? gt : src) + kh * STAGE_BYTES, STAGE_BYTES, &fullc[slot]);
+                  }
                   if (++slot == nst) { slot = 0; ph ^= 1; }
                 }
                 continue;
@@ -471,42 +483,44 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
           uint64_t* fullc = full + c * MAX_STAGES;
           uint64_t* emptyc = empty + c * MAX_STAGES;
           const unsigned char* ringc = s.ring + c * nst * STAGE_BYTES;
-          if (optype == 2) {
-            // B3 = dE/dx tile (A, shared memory) x W3 image (B, shared memory); stages as the producer queued them
-            constexpr int NS = (F16 && !X3) ? 2 : 4;
-            uint32_t sb[NS];
-            int sl[NS];
-#pragma unroll
-            for (int i = 0; i < NS; ++i) {
-              sl[i] = slot[c];
-              mbar_wait(&fullc[sl[i]], ph[c]);
-              sb[i] = smem_u32(ringc + sl[i] * STAGE_BYTES);
-              if (++slot[c] == nst) { slot[c] = 0; ph[c] ^= 1; }
-            }
-            tc_fence_after();
+          if (xl2 && optype == 2) {
+            // B3 = dE/dx tile (A, shared memory) x W3 image (B, shared memory); (W, G) stage pairs as the producer
+            // queued them.  Both images: K-major, 16-byte core-matrix rows, 128 rows per k-chunk (LBO 2048, SBO 128).
+            constexpr int NPAIR = (F16 && !X3) ? 1 : 2;
             const uint32_t dcol = chain + oi.d_col;
-            // both images: K-major, 16-byte core-matrix rows, 128 rows per k-chunk (LBO 2048 B, SBO 128 B)
-            if (!F16) {
 #pragma unroll
-              for (int ks = 0; ks < 8; ++ks) {   // K = 8 per MMA: two k-chunks of 4 floats; W0 G0 hold k < 32
-                const uint32_t off = uint32_t(ks & 3) * 4096u;
-                umma_tf32_ss_elect(dcol, umma_smem_desc(sb[(ks >> 2) * 2 + 1] + off, 2048u, 128u),
-                                   umma_smem_desc(sb[(ks >> 2) * 2] + off, 2048u, 128u), idesc, ks ? 1u : 0u, leader);
+            for (int pr = 0; pr < NPAIR; ++pr) {
+              const int s_w = slot[c];
+              mbar_wait(&fullc[s_w], ph[c]);
+              if (++slot[c] == nst) { slot[c] = 0; ph[c] ^= 1; }
+              const int s_g = slot[c];
+              mbar_wait(&fullc[s_g], ph[c]);
+              if (++slot[c] == nst) { slot[c] = 0; ph[c] ^= 1; }
+              tc_fence_after();
+              const uint32_t wb = smem_u32(ringc + s_w * STAGE_BYTES), gb = smem_u32(ringc + s_g * STAGE_BYTES);
+              if (!F16) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)   // K = 8 per MMA: two k-chunks of 4 floats
+                  umma_tf32_ss_elect(dcol, umma_smem_desc(gb + uint32_t(ks) * 4096u, 2048u, 128u),
+                                     umma_smem_desc(wb + uint32_t(ks) * 4096u, 2048u, 128u), idesc, (pr | ks) ? 1u : 0u, leader);
+              } else if (X3) {
+#pragma unroll
+                for (int term = 0; term < 3; ++term) {   // Ghi Whi, Glo Whi, Ghi Wlo; lo halves sit 8 KB into the stage
+                  const uint32_t a_s = gb + (term == 1 ? 8192u : 0u), b_s = wb + (term == 2 ? 8192u : 0u);
+#pragma unroll
+                  for (int ks = 0; ks < 2; ++ks)         // K = 16 per MMA: two k-chunks of 8 halves
+                    umma_f16_ss_elect(dcol, umma_smem_desc(a_s + uint32_t(ks) * 4096u, 2048u, 128u),
+                                      umma_smem_desc(b_s + uint32_t(ks) * 4096u, 2048u, 128u), idesc, (pr | term | ks) ? 1u : 0u, leader);
+                }
+              } else {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                  umma_f16_ss_elect(dcol, umma_smem_desc(gb + uint32_t(ks) * 4096u, 2048u, 128u),
+                                    umma_smem_desc(wb + uint32_t(ks) * 4096u, 2048u, 128u), idesc, ks ? 1u : 0u, leader);
               }
-            } else {
-#pragma unroll
-              for (int term = 0; term < (X3 ? 3 : 1); ++term) {
-                // 3-term: Ghi Whi, Glo Whi, Ghi Wlo  (stages: 0 Whi, 1 Ghi, 2 Glo, 3 Wlo)
-                const uint32_t a_s = X3 ? sb[term == 1 ? 2 : 1] : sb[1];
-                const uint32_t b_s = X3 ? sb[term == 2 ? 3 : 0] : sb[0];
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks)   // K = 16 per MMA: two k-chunks of 8 halves
-                  umma_f16_ss_elect(dcol, umma_smem_desc(a_s + uint32_t(ks) * 4096u, 2048u, 128u),
-                                    umma_smem_desc(b_s + uint32_t(ks) * 4096u, 2048u, 128u), idesc, (term | ks) ? 1u : 0u, leader);
-              }
+              umma_commit_elect(&emptyc[s_w], leader);
+              umma_commit_elect(&emptyc[s_g], leader);
             }
-#pragma unroll
-            for (int i = 0; i < NS; ++i) umma_commit_elect(&emptyc[sl[i]], leader);
           } else
           for (int st = 0; st < (X3 ? 2 : 1) * oi.nstages; ++st) {
             if (!mbar_test(&fullc[slot[c]], ph[c])) { STAT_T0(); mbar_wait(&fullc[slot[c]], ph[c]); STAT_ADD(w_full); }
@@ -575,8 +589,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
     // this CTA's slice of the L2-resident workspace (tc_ws_cta_words): ReLU masks, both end-point outputs of
     // every segment, and the dE/dx operand tiles one fused pass builds from them for the backward items
     uint32_t* maskws = reinterpret_cast<uint32_t*>(p.workspace) + tc_queue_words(p.N) + size_t(blockIdx.x) * tc_ws_cta_words(K, M, W);
-    float* X1 = reinterpret_cast<float*>(maskws + size_t(K + 16) * 512);
-    float* X2 = X1 + size_t(M) * W * XD_STRIDE;
+    float* X1g = reinterpret_cast<float*>(maskws + size_t(K + 16) * 512);
+    float* X1 = xl2 ? X1g : s.XD;   // left-end outputs, then the differences: shared memory when they fit
+    float* X2 = X1g + size_t(M) * W * XD_STRIDE;
     unsigned char* Gt = reinterpret_cast<unsigned char*>(X2 + size_t(M) * W * XD_STRIDE);
 
     for (int i = t512; i < 4 * n_poly * Kb; i += EPI_THREADS) s.basis[i] = p.basis[i];
@@ -612,6 +627,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
       }
       const float2 pa = make_float2(p.a[2 * n], p.a[2 * n + 1]);
       const float2 pb = make_float2(p.b[2 * n], p.b[2 * n + 1]);
+      int dec_base = p.dec_base ? p.dec_base[n] : 0;
+      if (dec_base < 0 || dec_base + K > p.K_total) {   // memory safety; reported through the status word
+        dec_base = 0;
+        if (t512 == 0) atomicOr(&queue[1], unsigned(VLG_STATUS_BAD_PACKED));
+      }
       named_bar(3, EPI_THREADS);
 
       for (int step = step_lo; step < step_hi; ++step) {
@@ -716,6 +736,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
             for (int k = 0; k < K; ++k)
               for (int q = 0; q * 128 < s.cnt[k]; ++q) ctl->item[ni++] = uint16_t(k | (q << 8));
             ctl->nitems = ni;
+            ctl->base = dec_base;
             n_items += unsigned(ni);
             for (int k = 0; k < K; ++k) n_rows += unsigned(s.cnt[k]);
             __threadfence_block();
@@ -883,16 +904,48 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
           }
           named_bar(3, EPI_THREADS);
 
-          // ============ x2 - x1: the energy and the dE/dx operand tiles of the backward items ============
+          // ============ x2 - x1, the energy, and the dE/dx operand tiles of the backward items ============
           if (GRAD) {
-            // One task = (item, row, 8 output columns): G = (2/M) * [ sum over the segments whose RIGHT end is this
-            // (point, decoder) of (x2 - x1)  -  sum over those whose LEFT end it is of (x2 - x1) ], written as one 16-byte
-            // piece of the item's K-major operand tile in the workspace (fp16; 3-term mode: hi and lo tiles; tf32: two
-            // 16-byte pieces of fp32).  The producer then brings a whole tile into shared memory with ONE bulk copy and
-            // B3 runs with its A operand from shared memory: no per-item dE/dx build, no epilogue round trip before B3.
-            // A segment's squared length is counted by the row at its left end (exactly one): the energy, in a fixed order.
+            // (1) The valid rows of one MC sample are contiguous in both buffers: a flat, fully coalesced pass over
+            // 16-byte pieces (x2 from the workspace, x1 from shared memory or the workspace, the difference back in
+            // place of x1), four independent pieces per thread in flight.  The energy is the plain sum of squares,
+            // in a fixed order (deterministic).
             float e = 0.f;
-            const int ntask = nitems * 1024;
+            const int n4 = nseg * (XD_STRIDE / 4);
+            for (int m = 0; m < M; ++m) {
+              const float4* x2 = reinterpret_cast<const float4*>(X2 + m * W * XD_STRIDE);
+              float4* x1 = reinterpret_cast<float4*>(X1 + m * W * XD_STRIDE);
+              for (int i0 = t512; i0 < n4; i0 += 4 * EPI_THREADS) {
+                float4 v[4], u[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const int i = i0 + j * EPI_THREADS;
+                  v[j] = i < n4 ? __ldcg(x2 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                  if (xl2) u[j] = i < n4 ? __ldcg(x1 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const int i = i0 + j * EPI_THREADS;
+                  if (i < n4) {
+                    if (!xl2) u[j] = x1[i];
+                    const float4 a = make_float4(v[j].x - u[j].x, v[j].y - u[j].y, v[j].z - u[j].z, v[j].w - u[j].w);
+                    x1[i] = a;
+                    e = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(a.z, a.z, fmaf(a.w, a.w, e))));
+                  }
+                }
+              }
+            }
+            e = warp_sum(e);
+            if (lane == 0) s.red[320 + ew] = e;
+            named_bar(3, EPI_THREADS);  // the differences are read by other threads below
+            // (2) [only when the differences live in the workspace, xl2: from shared memory the backward items build
+            // their dE/dx rows themselves -- inside an item the other chain hides the latency, a CTA-wide pass cannot;
+            // measured 411 k vs 349 k spline-steps/s on the headline shape.]  One task = (item, row, 8 output columns): G = (2/M) * [sum over the segments whose RIGHT end is this
+            // (point, decoder) of (x2 - x1)  -  sum over those whose LEFT end it is], written as one 16-byte piece of
+            // the item's K-major operand tile in the workspace (fp16; 3-term mode: hi and lo tiles; tf32: two 16-byte
+            // pieces of fp32).  The producer brings a tile into shared memory with bulk copies and B3 runs with its A
+            // operand from shared memory: no per-item dE/dx build, no epilogue round trip in front of B3.
+            const int ntask = xl2 ? nitems * 1024 : 0;
             const float gsc = F16 ? coefm * F16_GRAD_SCALE : coefm;
             for (int t0 = t512; t0 < ntask; t0 += EPI_THREADS) {
               const int it = t0 >> 10, c = (t0 >> 7) & 7, r = t0 & 127;
@@ -904,36 +957,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
               for (int j = 0; j < 8; ++j) g[j] = 0.f;
               if (c < 7) {
                 const bool wide = c < 6;   // chunk 6 = columns 48..51 (+ zero padding up to 55)
+                float4 dd[2 * TC_MAX_M][2];
+                bool on[2 * TC_MAX_M];
 #pragma unroll
                 for (int m = 0; m < TC_MAX_M; ++m) {
-                  if (m >= M) break;
-                  const bool right = pt >= 1 && s.sel[(m * 2 + 1) * W + pt - 1] == k;
-                  const bool left = s.sel[(m * 2 + 0) * W + pt] == k;
-                  float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, b0 = a0, b1 = a0, c0 = a0, c1 = a0, d0 = a0, d1 = a0;
-                  const size_t offl = size_t(m * W + pt) * XD_STRIDE + 8 * c, offr = offl - XD_STRIDE;   // offr only if pt >= 1
-                  if (right) {
-                    a0 = __ldcg(reinterpret_cast<const float4*>(X2 + offr));
-                    b0 = __ldcg(reinterpret_cast<const float4*>(X1 + offr));
-                    if (wide) {
-                      a1 = __ldcg(reinterpret_cast<const float4*>(X2 + offr + 4));
-                      b1 = __ldcg(reinterpret_cast<const float4*>(X1 + offr + 4));
+                  on[2 * m] = m < M && pt >= 1 && s.sel[(m * 2 + 1) * W + pt - 1] == k;   // right end of segment pt-1
+                  on[2 * m + 1] = m < M && s.sel[(m * 2 + 0) * W + pt] == k;              // left end of segment pt
+                }
+#pragma unroll
+                for (int j = 0; j < 2 * TC_MAX_M; ++j) {      // all loads first (L2 latency when xl2)
+                  const float* src = X1 + ptrdiff_t((j >> 1) * W + pt - 1 + (j & 1)) * XD_STRIDE + 8 * c;   // dereferenced only if on[j]
+                  dd[j][0] = dd[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                  if (on[j]) {
+                    if (xl2) {
+                      dd[j][0] = __ldcg(reinterpret_cast<const float4*>(src));
+                      if (wide) dd[j][1] = __ldcg(reinterpret_cast<const float4*>(src) + 1);
+                    } else {
+                      dd[j][0] = *reinterpret_cast<const float4*>(src);
+                      if (wide) dd[j][1] = *(reinterpret_cast<const float4*>(src) + 1);
                     }
                   }
-                  if (left) {
-                    c0 = __ldcg(reinterpret_cast<const float4*>(X2 + offl));
-                    d0 = __ldcg(reinterpret_cast<const float4*>(X1 + offl));
-                    if (wide) {
-                      c1 = __ldcg(reinterpret_cast<const float4*>(X2 + offl + 4));
-                      d1 = __ldcg(reinterpret_cast<const float4*>(X1 + offl + 4));
-                    }
-                  }
-                  g[0] += a0.x - b0.x; g[1] += a0.y - b0.y; g[2] += a0.z - b0.z; g[3] += a0.w - b0.w;
-                  g[4] += a1.x - b1.x; g[5] += a1.y - b1.y; g[6] += a1.z - b1.z; g[7] += a1.w - b1.w;
-                  const float l0 = c0.x - d0.x, l1 = c0.y - d0.y, l2 = c0.z - d0.z, l3 = c0.w - d0.w;
-                  const float l4 = c1.x - d1.x, l5 = c1.y - d1.y, l6 = c1.z - d1.z, l7 = c1.w - d1.w;
-                  g[0] -= l0; g[1] -= l1; g[2] -= l2; g[3] -= l3; g[4] -= l4; g[5] -= l5; g[6] -= l6; g[7] -= l7;
-                  e = fmaf(l0, l0, fmaf(l1, l1, fmaf(l2, l2, fmaf(l3, l3, e))));
-                  e = fmaf(l4, l4, fmaf(l5, l5, fmaf(l6, l6, fmaf(l7, l7, e))));
+                }
+#pragma unroll
+                for (int j = 0; j < 2 * TC_MAX_M; ++j) {
+                  const float sg = (j & 1) ? -1.f : 1.f;
+                  g[0] = fmaf(sg, dd[j][0].x, g[0]); g[1] = fmaf(sg, dd[j][0].y, g[1]);
+                  g[2] = fmaf(sg, dd[j][0].z, g[2]); g[3] = fmaf(sg, dd[j][0].w, g[3]);
+                  g[4] = fmaf(sg, dd[j][1].x, g[4]); g[5] = fmaf(sg, dd[j][1].y, g[5]);
+                  g[6] = fmaf(sg, dd[j][1].z, g[6]); g[7] = fmaf(sg, dd[j][1].w, g[7]);
                 }
               }
 #pragma unroll
@@ -959,9 +1010,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                 *reinterpret_cast<uint4*>(tile + ((2 * c + 1) * 128 + r) * 16) = v1;
               }
             }
-            fence_proxy_async_all();   // the tiles are read by the TMA engine (async proxy)
-            e = warp_sum(e);
-            if (lane == 0) s.red[320 + ew] = e;
+            if (xl2) fence_proxy_async_all();   // the tiles are read by the TMA engine (async proxy)
           } else {
             // forward-only kernel (also reports the polyline length, a sum of per-segment norms): 16 lanes
             // per (m, segment) entry, one 16-byte piece each; six entries per lane in flight.
@@ -984,7 +1033,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                 const bool ok = ent < nent && (ent % W) < nseg && sub < NV;
                 float q = 0.f;
                 if (ok) {
-                  const float4 u = __ldcg(reinterpret_cast<const float4*>(X1 + ent * XD_STRIDE) + sub);
+                  const float4* up = reinterpret_cast<const float4*>(X1 + ent * XD_STRIDE) + sub;
+                  const float4 u = xl2 ? __ldcg(up) : *up;
                   const float4 a = make_float4(v[j].x - u.x, v[j].y - u.y, v[j].z - u.z, v[j].w - u.w);
                   q = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(a.z, a.z, a.w * a.w)));
                 }
@@ -999,7 +1049,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
           }
           if (GRAD) {
             named_bar(3, EPI_THREADS);            // every tile of the window is written (and fenced for the async proxy)
-            if (t512 == 0) mbar_arrive(g_ready);  // -> the producers may bring them into shared memory
+            if (xl2 && t512 == 0) mbar_arrive(g_ready);  // -> the producers may bring them into shared memory
           }
 
           if (GRAD) {
@@ -1018,11 +1068,61 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
               // mask words for E-B3 (the L2 round trip overlaps the first MMA)
               uint2 bits = make_uint2(0u, 0u);
               if (active) bits = *reinterpret_cast<const uint2*>(maskws + (it * 128 + row) * 4 + half * 2);
-              // B3 takes its A operand (the dE/dx tile) from shared memory: nothing to build here.  This arrive
-              // only tells the issuer that the chain's accumulator columns are free (all tcgen05.ld of the
-              // previous item are complete in program order).
-              tc_fence_before();
-              mbar_arrive(&a_ready[chain_id]);
+              if (xl2) {
+                // B3 takes its A operand (the dE/dx tile) from shared memory: nothing to build here.  This arrive
+                // only tells the issuer that the chain's accumulator columns are free (all tcgen05.ld of the
+                // previous item are complete in program order).
+                tc_fence_before();
+                mbar_arrive(&a_ready[chain_id]);
+              } else {
+                // G = dE/dx_k (this point), columns xc0 .. xc0+31 -> X[xc0 : xc0+32]
+                if (wact) {
+                  float g[32];
+  #pragma unroll
+                  for (int j = 0; j < 32; ++j) g[j] = 0.f;
+                  for (int m = 0; m < (active ? M : 0); ++m) {
+                    if (pt >= 1 && s.sel[(m * 2 + 1) * W + pt - 1] == k) {
+                      const float4* d = reinterpret_cast<const float4*>(X1 + (m * W + pt - 1) * XD_STRIDE + xc0);
+  #pragma unroll
+                      for (int q = 0; q < 8; ++q)
+                        if (q < nq) {
+                          const float4 v = d[q];
+                          g[4 * q] += v.x; g[4 * q + 1] += v.y; g[4 * q + 2] += v.z; g[4 * q + 3] += v.w;
+                        }
+                    }
+                    if (s.sel[(m * 2 + 0) * W + pt] == k) {
+                      const float4* d = reinterpret_cast<const float4*>(X1 + (m * W + pt) * XD_STRIDE + xc0);
+  #pragma unroll
+                      for (int q = 0; q < 8; ++q)
+                        if (q < nq) {
+                          const float4 v = d[q];
+                          g[4 * q] -= v.x; g[4 * q + 1] -= v.y; g[4 * q + 2] -= v.z; g[4 * q + 3] -= v.w;
+                        }
+                    }
+                  }
+                  if (F16) {
+                    uint32_t v[16], vl[X3 ? 16 : 1];
+  #pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                      const float g0 = (coefm * F16_GRAD_SCALE) * g[2 * j], g1 = (coefm * F16_GRAD_SCALE) * g[2 * j + 1];
+                      if (X3)
+                        pack_hilo_h2(g0, g1, v[j], vl[j]);
+                      else
+                        v[j] = pack_h2(g0, g1);
+                    }
+                    tmem_st16(colX + half * 16, v);
+                    if (X3) tmem_st16(colX + 64 + half * 16, reinterpret_cast<uint32_t(&)[16]>(vl));
+                  } else {
+                    uint32_t v[32];
+  #pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = tf32_round_bits(__float_as_uint(coefm * g[j]));
+                    tmem_st32(colX + xc0, v);
+                  }
+                }
+                tmem_wait_st();
+                tc_fence_before();
+                mbar_arrive(&a_ready[chain_id]);
+              }
               // dh2 = (G W3) * mask2 -> A4 (Y, in place)
               { STAT_T0(); acc_wait(&acc_ready[chain_id], ph_acc, lane); STAT_ADD(w_acc); }
               ph_acc ^= 1;
@@ -1210,42 +1310,53 @@ static int tc_grid(int N) {
   return N < sms ? N : sms;
 }
 
-// Window length: as few 128-row items per curve as possible.  A decoder is drawn by a point with
+// Launch plan.  Window length: as few 128-row items per curve as possible.  A decoder is drawn by a point with
 // probability p = 1 - (1 - 1/K)^(2M); its row count n in a window of W points is ~Binomial(W, p) and it
-// costs ceil(n/128) items.  Evaluate the expected item count for every admissible number of windows.
-static int tc_window_points(int T, int K, int M) {
+// costs ceil(n/128) items.  Evaluate the expected item count for every admissible number of windows, for both
+// homes of the left-end outputs / differences: shared memory (xl2 = 0; 208 M bytes per point limit the window)
+// or the L2-resident workspace (xl2 = 1; any window up to TC_MAX_W points, but the dE/dx tile pass then sits on
+// L2 latency: measured +45 % per item on the headline shape).
+struct TcPlan {
+  int W, nst, xl2;
+};
+static TcPlan tc_plan(int T, int K, int M) {
   const double p = 1.0 - pow(1.0 - 1.0 / K, 2.0 * M);
   const int segs = T - 1;
-  if (const char* env = getenv("VLG_TC_WINDOW")) {  // tuning override: number of windows per curve
-    const int nwin = atoi(env);
-    if (nwin >= 1) {
-      const int w = (segs + nwin - 1) / nwin + 1;
-      if (w >= 2 && w <= TC_MAX_W && tc_stages(w, K, M) >= 4) return w;
+  int force_nwin = 0, force_xl2 = -1;
+  if (const char* env = getenv("VLG_TC_WINDOW")) force_nwin = atoi(env);   // tuning overrides
+  if (const char* env = getenv("VLG_TC_XL2")) force_xl2 = atoi(env);
+  TcPlan best = {0, 0, 0};
+  double best_cost = 1e300;
+  for (int xl2 = 0; xl2 < 2; ++xl2) {
+    if (force_xl2 >= 0 && xl2 != force_xl2) continue;
+    for (int nwin = 1; nwin <= segs; ++nwin) {
+      const int w = (segs + nwin - 1) / nwin + 1;  // points per window
+      if (force_nwin >= 1 && nwin != force_nwin) {
+        if (w <= 128) break;
+        continue;
+      }
+      if (w <= TC_MAX_W) {
+        const int nst = tc_stages(w, K, M, xl2);
+        if (nst >= 2) {
+          const double mean = w * p, sd = sqrt(w * p * (1.0 - p)) + 1e-9;
+          double items = 0.0;
+          for (int q = 0; q * 128 < w; ++q) items += 0.5 * erfc((q * 128 + 0.5 - mean) / (sd * 1.4142135623730951));  // P(n > 128 q)
+          double cost = nwin * (K * items + 0.35);  // + per-window fixed cost in item units
+          if (nst == 2) cost *= 1.04;               // a two-stage weight ring cannot hold a whole GEMM's weights
+          if (xl2) cost *= 1.45;
+          if (cost < best_cost) { best_cost = cost; best = {w, nst, xl2}; }
+        }
+      }
+      if (w <= 128) break;
     }
   }
-  int best_w = 0;
-  double best = 1e300;
-  for (int nwin = 1; nwin <= segs; ++nwin) {
-    const int w = (segs + nwin - 1) / nwin + 1;  // points per window
-    if (w > TC_MAX_W) continue;
-    const int nst = tc_stages(w, K, M);
-    if (nst >= 4) {   // B3 of the tf32 / 3-term kernels holds four stages at once
-      const double mean = w * p, sd = sqrt(w * p * (1.0 - p)) + 1e-9;
-      double items = 0.0;
-      for (int q = 0; q * 128 < w; ++q) items += 0.5 * erfc((q * 128 + 0.5 - mean) / (sd * 1.4142135623730951));  // P(n > 128 q)
-      double cost = nwin * (K * items + 0.35);  // + per-window fixed cost in item units
-      if (cost < best) { best = cost; best_w = w; }
-    }
-    if (w <= 128) break;
-  }
-  return best_w;  // 0: does not fit
+  return best;  // W == 0: does not fit
 }
 
-// per CTA: layer-2 ReLU mask bits [K+16 items][128 rows][4 words] + right-end outputs x2 [M][W][52] fp32
 size_t tc_workspace_bytes(int N, int T, int K, int M) {
   if (M > TC_MAX_M || K > TC_MAX_K) return 0;
-  const int W = tc_window_points(T, K, M);
-  return tc_queue_words(N) * 4 + size_t(tc_grid(N)) * tc_ws_cta_words(K, M, W) * 4;
+  const TcPlan pl = tc_plan(T, K, M);
+  return tc_queue_words(N) * 4 + size_t(tc_grid(N)) * tc_ws_cta_words(K, M, pl.W) * 4;
 }
 
 #ifdef VLG_TC_STATS
@@ -1258,12 +1369,11 @@ cudaError_t launch_tc(const StepParams& p, bool grad, cudaStream_t stream) {
   if (p.precision < 1 || p.precision > 3) return cudaErrorNotSupported;
   const int fmt = p.precision == 1 ? FMT_TF32 : p.precision == 3 ? FMT_F16 : FMT_F16X3;
   if (p.M > TC_MAX_M || p.K > TC_MAX_K) return cudaErrorNotSupported;
-  const int W = tc_window_points(p.T, p.K, p.M);
-  if (W < 2) return cudaErrorNotSupported;
-  const int nst = tc_stages(W, p.K, p.M);
-  if (nst < 4) return cudaErrorNotSupported;
+  const TcPlan pl = tc_plan(p.T, p.K, p.M);
+  const int W = pl.W, nst = pl.nst, xl2 = pl.xl2;
+  if (W < 2 || nst < 2) return cudaErrorNotSupported;
   if (p.workspace == nullptr || p.workspace_bytes < tc_workspace_bytes(p.N, p.T, p.K, p.M)) return cudaErrorInvalidValue;
-  const size_t smem = tc_smem_fixed_bytes(W, p.K, p.M) + size_t(2) * nst * STAGE_BYTES;
+  const size_t smem = tc_smem_fixed_bytes(W, p.K, p.M, xl2) + size_t(2) * nst * STAGE_BYTES;
   const int grid = tc_grid(p.N);
   StepParams q = p;
   // chunks of a curve per launch: at least 4, and enough work units (~48 per CTA) that the last wave's
@@ -1280,11 +1390,15 @@ cudaError_t launch_tc(const StepParams& p, bool grad, cudaStream_t stream) {
     kernel<<<grid, TC_THREADS, smem, stream>>>(q, nst, W);
     return cudaGetLastError();
   };
-  if (grad)
-    return fmt == FMT_TF32 ? launch(tc_curve_kernel<true, FMT_TF32>)
-           : fmt == FMT_F16 ? launch(tc_curve_kernel<true, FMT_F16>) : launch(tc_curve_kernel<true, FMT_F16X3>);
-  return fmt == FMT_TF32 ? launch(tc_curve_kernel<false, FMT_TF32>)
-         : fmt == FMT_F16 ? launch(tc_curve_kernel<false, FMT_F16>) : launch(tc_curve_kernel<false, FMT_F16X3>);
+  auto by_fmt = [&](auto grad_c, auto xl2_c) -> cudaError_t {
+    constexpr bool G = decltype(grad_c)::value, X = decltype(xl2_c)::value;
+    return fmt == FMT_TF32 ? launch(tc_curve_kernel<G, FMT_TF32, X>)
+           : fmt == FMT_F16 ? launch(tc_curve_kernel<G, FMT_F16, X>) : launch(tc_curve_kernel<G, FMT_F16X3, X>);
+  };
+  using T_ = std::true_type;
+  using F_ = std::false_type;
+  if (grad) return xl2 ? by_fmt(T_{}, T_{}) : by_fmt(T_{}, F_{});
+  return xl2 ? by_fmt(F_{}, T_{}) : by_fmt(F_{}, F_{});
 }
 
 }  // namespace vlg

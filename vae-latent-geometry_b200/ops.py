@@ -89,7 +89,8 @@ def workspace_status(workspace: torch.Tensor) -> int:
 def optimize_steps(packed: torch.Tensor, k_total: int, x_dim: int, k_active: int, n_poly: int, M: int, steps: int, step0: int,
                    a: torch.Tensor, b: torch.Tensor, omega: torch.Tensor, adam_m: torch.Tensor,
                    adam_v: torch.Tensor, basis: torch.Tensor, t: torch.Tensor,
-                   draws: Optional[torch.Tensor], seed: int, curve_id0: int, lr: float, beta1: float,
+                   draws: Optional[torch.Tensor], decoder_base: Optional[torch.Tensor], seed: int, curve_id0: int,
+                   lr: float, beta1: float,
                    beta2: float, eps: float, penalty_w: float, energy_last: torch.Tensor,
                    energy_trace: Optional[torch.Tensor], precision: int,
                    workspace: Optional[torch.Tensor]) -> None:
@@ -102,6 +103,7 @@ def optimize_steps(packed: torch.Tensor, k_total: int, x_dim: int, k_active: int
             _chk(adam_m, "adam_m", shape=(N, Kb, 2)), _chk(adam_v, "adam_v", shape=(N, Kb, 2)),
             _chk(basis, "basis", shape=(4 * n_poly, Kb)), _chk(t, "t", shape=(T,)),
             _chk(draws, "draws", dtype=torch.uint8, shape=(N, steps, M, 2, T - 1)) if draws is not None else 0,
+            _chk(decoder_base, "decoder_base", dtype=torch.int32, shape=(N,)) if decoder_base is not None else 0,
             seed & 0xFFFFFFFFFFFFFFFF, curve_id0, lr, beta1, beta2, eps, penalty_w,
             _chk(energy_last, "energy_last", shape=(N,)),
             _chk(energy_trace, "energy_trace", shape=(steps, N)) if energy_trace is not None else 0,
@@ -115,7 +117,7 @@ def optimize_steps(packed: torch.Tensor, k_total: int, x_dim: int, k_active: int
 @torch.library.custom_op("vlg::curve_energy", mutates_args=("energy", "length", "workspace"))
 def curve_energy(packed: torch.Tensor, k_total: int, x_dim: int, k_active: int, n_poly: int, M: int, a: torch.Tensor,
                  b: torch.Tensor, omega: torch.Tensor, basis: torch.Tensor, t: torch.Tensor,
-                 draws: Optional[torch.Tensor], seed: int, curve_id0: int, step: int,
+                 draws: Optional[torch.Tensor], decoder_base: Optional[torch.Tensor], seed: int, curve_id0: int, step: int,
                  energy: torch.Tensor, length: Optional[torch.Tensor], precision: int,
                  workspace: Optional[torch.Tensor]) -> None:
     N, Kb = omega.shape[0], omega.shape[1]
@@ -126,6 +128,7 @@ def curve_energy(packed: torch.Tensor, k_total: int, x_dim: int, k_active: int, 
             _chk(a, "a", shape=(N, 2)), _chk(b, "b", shape=(N, 2)), _chk(omega, "omega", shape=(N, Kb, 2)),
             _chk(basis, "basis", shape=(4 * n_poly, Kb)), _chk(t, "t", shape=(T,)),
             _chk(draws, "draws", dtype=torch.uint8, shape=(N, 1, M, 2, T - 1)) if draws is not None else 0,
+            _chk(decoder_base, "decoder_base", dtype=torch.int32, shape=(N,)) if decoder_base is not None else 0,
             seed & 0xFFFFFFFFFFFFFFFF, curve_id0, step, _chk(energy, "energy", shape=(N,)),
             _chk(length, "length", shape=(N,)) if length is not None else 0, precision,
             _chk(workspace, "workspace", dtype=torch.uint8) if workspace is not None else 0,
