@@ -73,10 +73,13 @@ constexpr int MAX_STAGES = 5;         // per chain
 constexpr int XD_STRIDE = 52;         // floats per stored decoder output row (X <= 52; 16 B rows)
 constexpr int GT_BYTES = 32768;       // dE/dx operand tile of one item in the workspace: fp16 16 KB (3-term: hi tile + lo tile),
                                       // tf32 32 KB; canonical no-swizzle K-major image [k-chunk][row][16 B], like the weights
-constexpr int TC_MAX_W = 512;         // curve points per window (runtime W <= this); neighbouring windows share one point
+constexpr int TC_MAX_W = 512;         // points per window, one curve per window (neighbouring windows share one point)
+constexpr int TC_MAX_WG = 2048;       // points per window when it holds several whole curves (XL2 kernels)
+constexpr int TC_MAX_G = 8;           // curves per window (XL2 kernels)
+constexpr int OM_STRIDE = 6 * MAX_KB + 2;   // per-curve omega | adam m | adam v
 constexpr int TC_MAX_M = 2;           // MC samples supported by this kernel
 constexpr int TC_MAX_K = 64;          // decoders
-constexpr int MAX_ITEMS = TC_MAX_K + 16;  // sum_k ceil(n_k/128) <= K + 2*M*W/128
+constexpr int MAX_ITEMS = TC_MAX_K + 2 * TC_MAX_M * TC_MAX_WG / 128 + 8;  // sum_k ceil(n_k/128) <= K + 2*M*W/128
 
 // the four tensor-core GEMMs of one decoder
 struct OpInfo {
@@ -192,11 +195,13 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
 // + one progress word per curve, 256 B aligned
 __host__ __device__ inline size_t tc_queue_words(int N) { return (size_t(64 + N) + 63) / 64 * 64; }
 
-// Per-CTA slice of the L2-resident workspace, in 32-bit words: layer-2 ReLU masks [K+16 items][128 rows][4],
+// Per-CTA slice of the L2-resident workspace, in 32-bit words: layer-2 ReLU masks [items][128 rows][4],
 // left-end decoder outputs x1 [M][W][52] and right-end outputs x2 [M][W][52] (fp32), dE/dx operand tiles
-// [K+16 items][GT_BYTES].  (K + 16 >= sum_k ceil(n_k / 128) for W <= 512, M <= 2.)
+// [items][GT_BYTES]; items = tc_max_items >= sum_k ceil(n_k / 128).
+__host__ __device__ inline int tc_max_items(int K, int M, int W) { return K + 2 * M * W / 128 + 2; }
 __host__ __device__ inline size_t tc_ws_cta_words(int K, int M, int W) {
-  return (size_t(K + 16) * 512 + 2 * size_t(M) * W * XD_STRIDE + size_t(K + 16) * (GT_BYTES / 4) + 31) / 32 * 32;
+  const size_t items = size_t(tc_max_items(K, M, W));
+  return (items * 512 + 2 * size_t(M) * W * XD_STRIDE + items * (GT_BYTES / 4) + 31) / 32 * 32;
 }
 
 struct WinCtl {
@@ -222,20 +227,24 @@ __device__ __forceinline__ void acc_wait(uint64_t* bar, uint32_t parity, int lan
 
 struct TcSmem {
   unsigned char* ring;  // [chain][stage] 16 KB
-  uint8_t* sel;         // [m][role][W] drawn decoder per segment
-  uint16_t* rows;       // [K][W] points of the window that drew decoder k, in increasing point order
-  uint16_t* wcnt;       // [K][16] rows of decoder k owned by each epilogue warp (then: exclusive prefix)
+  float* XD;            // [m][W][52] left-end outputs x1, then x2 - x1 (only when they fit: XL2 == 0; else in the workspace)
+  uint8_t* sel;         // [m][role][W] drawn decoder per segment (255: no segment)
+  uint16_t* rows;       // points of the window that drew decoder k, in increasing point order: rows[roff[k] .. + cnt[k])
+  uint16_t* wcnt;       // [K][chunks of 512 points][16 warps] rows per (decoder, chunk, warp) (then: exclusive prefix)
   int* cnt;             // [K]
+  int* roff;            // [K]
   WinCtl* ctl;          // [2] item lists, double buffered by window parity
-  float* XD;            // [m][W][52] left-end outputs x1, then x2 - x1 (only when they fit: xl2 == 0; else in the workspace)
   float* sw;            // [chain][SW_SLOTS] 576 floats: W1 (planar), b1, b2, b3 of an item's decoder
   float2* zs;           // W latent points of the window
-  float2* dzs;          // [chain][half][W]
-  float* coef;          // 64
+  float2* dzs;          // [4][W]: dz of point pt from the decoder of its draw slot (m0 left, m0 right, m1 left, m1 right)
+  float* coef;          // [G][64]
   float* basis;         // 288
-  float* om;            // 56
-  float* gacc;          // 20
-  float* red;           // 16*20 + 32
+  float* om;            // [G][OM_STRIDE]
+  float* gacc;          // [G][20]
+  float* pab;           // [G][4] end points a, b
+  float* etot;          // [G][2] energy / length of the step so far
+  float* red;           // [16][20] d(omega) partials per warp, then [G][32] energy | length partials per warp
+  float2* dzx;          // [chain][half][128] dz partial of a row's two half-threads (last backward item of the chain)
   uint64_t* bars;       // full[2][MAX_STAGES], empty[2][MAX_STAGES], a_ready[2], acc_ready[2], win_ready, sw_full[2][SW_SLOTS], ctl_free[2], g_ready
   uint32_t* tmem_base;  // [0] TMEM base address, [1] current work unit
 };
@@ -247,41 +256,55 @@ static_assert(TC_MAX_M == 2, "the row-list build tests four candidates per point
 
 // Fixed-size pieces first, at compile-time offsets from the start of dynamic shared memory (their
 // addresses fold into immediates -- the epilogue code is short of registers), then the window-sized
-// arrays, then the weight rings.
-constexpr int FIX_SW = 0;                                   // 2 chains x SW_SLOTS x 576
-constexpr int FIX_COEF = FIX_SW + 2 * SW_SLOTS * 576;       // 64
-constexpr int FIX_BASIS = FIX_COEF + 64;                    // 4 * MAX_NPOLY * MAX_KB
-constexpr int FIX_OM = FIX_BASIS + 4 * MAX_NPOLY * MAX_KB;  // 3 * 2 * MAX_KB + 2
-constexpr int FIX_GACC = FIX_OM + 3 * 2 * MAX_KB + 2;       // 2 * MAX_KB + 2
-constexpr int FIX_RED = FIX_GACC + 2 * MAX_KB + 2;          // 352
-constexpr int FIX_BARS = FIX_RED + 352;                     // BAR_WORDS (8-byte aligned)
-constexpr int FIX_TMEM = FIX_BARS + BAR_WORDS;              // 4
-constexpr int FIX_CTL = FIX_TMEM + 4;                       // CTL_FLOATS
-constexpr int FIX_CNT = FIX_CTL + CTL_FLOATS;               // TC_MAX_K
-constexpr int FIX_FLOATS = (FIX_CNT + TC_MAX_K + 3) / 4 * 4;  // XD starts 16-byte aligned
-static_assert(FIX_BARS % 2 == 0, "mbarriers need 8-byte alignment");
+// arrays, then the weight rings.  GM = curves per window the kernel is built for (1, or TC_MAX_G for XL2).
+template <int GM>
+struct Fix {
+  static constexpr int SW = 0;                                   // 2 chains x SW_SLOTS x 576
+  static constexpr int COEF = SW + 2 * SW_SLOTS * 576;           // GM x 64
+  static constexpr int BASIS = COEF + GM * 64;                   // 4 * MAX_NPOLY * MAX_KB
+  static constexpr int OM = BASIS + 4 * MAX_NPOLY * MAX_KB;      // GM x OM_STRIDE
+  static constexpr int GACC = OM + GM * OM_STRIDE;               // GM x 20
+  static constexpr int PAB = GACC + GM * 20;                     // GM x 4
+  static constexpr int ETOT = PAB + GM * 4;                      // GM x 2
+  static constexpr int RED = ETOT + GM * 2;                      // 320 + GM x 32
+  static constexpr int DZX = (RED + 320 + GM * 32 + 1) / 2 * 2;  // 2 x 2 x 128 float2
+  static constexpr int BARS = DZX + 1024;                         // BAR_WORDS (8-byte aligned)
+  static constexpr int TMEM = BARS + BAR_WORDS;                  // 4
+  static constexpr int CTL = TMEM + 4;                           // CTL_FLOATS
+  static constexpr int CNT = CTL + CTL_FLOATS;                   // TC_MAX_K
+  static constexpr int ROFF = CNT + TC_MAX_K;                    // TC_MAX_K
+  static constexpr int FLOATS = (ROFF + TC_MAX_K + 3) / 4 * 4;   // XD starts 16-byte aligned
+};
 
-__device__ __forceinline__ TcSmem tc_carve(unsigned char* base, int W, int K, int M, int xl2) {
+__host__ __device__ inline int tc_chunks(int W) { return (W + 511) / 512; }
+
+template <int GM>
+__device__ __forceinline__ TcSmem tc_carve(unsigned char* base, int W, int K, int M, bool xd_in_smem) {
+  using FX = Fix<GM>;
   TcSmem s;
   float* f = reinterpret_cast<float*>(base);
-  s.sw = f + FIX_SW;
-  s.coef = f + FIX_COEF;
-  s.basis = f + FIX_BASIS;
-  s.om = f + FIX_OM;
-  s.gacc = f + FIX_GACC;
-  s.red = f + FIX_RED;
-  s.bars = reinterpret_cast<uint64_t*>(f + FIX_BARS);
-  s.tmem_base = reinterpret_cast<uint32_t*>(f + FIX_TMEM);
-  s.ctl = reinterpret_cast<WinCtl*>(f + FIX_CTL);
-  s.cnt = reinterpret_cast<int*>(f + FIX_CNT);
-  f += FIX_FLOATS;
-  s.XD = f; f += xl2 ? 0 : M * W * XD_STRIDE;
+  s.sw = f + FX::SW;
+  s.coef = f + FX::COEF;
+  s.basis = f + FX::BASIS;
+  s.om = f + FX::OM;
+  s.gacc = f + FX::GACC;
+  s.pab = f + FX::PAB;
+  s.etot = f + FX::ETOT;
+  s.red = f + FX::RED;
+  s.dzx = reinterpret_cast<float2*>(f + FX::DZX);
+  s.bars = reinterpret_cast<uint64_t*>(f + FX::BARS);
+  s.tmem_base = reinterpret_cast<uint32_t*>(f + FX::TMEM);
+  s.ctl = reinterpret_cast<WinCtl*>(f + FX::CTL);
+  s.cnt = reinterpret_cast<int*>(f + FX::CNT);
+  s.roff = reinterpret_cast<int*>(f + FX::ROFF);
+  f += FX::FLOATS;
+  s.XD = f; f += xd_in_smem ? M * W * XD_STRIDE : 0;
   s.zs = reinterpret_cast<float2*>(f); f += 2 * W;
   s.dzs = reinterpret_cast<float2*>(f); f += 2 * 4 * W;
   s.sel = reinterpret_cast<uint8_t*>(f); f += TC_MAX_M * 2 * W / 4 + 1;
-  s.wcnt = reinterpret_cast<uint16_t*>(f); f += K * 8;
+  s.wcnt = reinterpret_cast<uint16_t*>(f); f += K * tc_chunks(W) * 8;
   s.rows = reinterpret_cast<uint16_t*>(f);
-  const size_t ring_off = (size_t(reinterpret_cast<unsigned char*>(f) - base) + size_t(K) * W * 2 + 127) / 128 * 128;
+  const size_t ring_off = (size_t(reinterpret_cast<unsigned char*>(f) - base) + size_t(2 * M) * W * 2 + 127) / 128 * 128;
   s.ring = base + ring_off;
   return s;
 }
@@ -290,9 +313,10 @@ __device__ __forceinline__ TcSmem tc_carve(unsigned char* base, int W, int K, in
 
 static size_t tc_smem_fixed_bytes(int W, int K, int M, int xl2) {
   // everything but the weight rings, in the order of tc_carve (+ alignment slack before the rings)
-  size_t fl = size_t(FIX_FLOATS) + (xl2 ? 0 : size_t(M) * W * XD_STRIDE) + 2 * size_t(W) + 2 * 4 * size_t(W) + TC_MAX_M * 2 * size_t(W) / 4 + 1 +
-              size_t(K) * 8;
-  return (fl * 4 + size_t(K) * W * 2 + 127) / 128 * 128;
+  const size_t fix = xl2 ? Fix<TC_MAX_G>::FLOATS : Fix<1>::FLOATS;
+  size_t fl = fix + (xl2 ? 0 : size_t(M) * W * XD_STRIDE) + 2 * size_t(W) + 2 * 4 * size_t(W) + TC_MAX_M * 2 * size_t(W) / 4 + 1 +
+              size_t(K) * tc_chunks(W) * 8;
+  return (fl * 4 + size_t(2 * M) * W * 2 + 127) / 128 * 128;
 }
 static int tc_stages(int W, int K, int M, int xl2) {
   const long budget = 232448 - long(tc_smem_fixed_bytes(W, K, M, xl2));
@@ -302,15 +326,18 @@ static int tc_stages(int W, int K, int M, int xl2) {
 }
 
 template <bool GRAD, int FMT, bool XL2>
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, int nst, int W) {
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, int nst, int W, int G_) {
   constexpr bool xl2 = XL2;               // left-end outputs / differences in the L2 workspace instead of shared memory
+  constexpr int GM = XL2 ? TC_MAX_G : 1;  // curves per window this kernel is built for
+  const int G = XL2 ? G_ : 1;             // curves per window of this launch: G > 1 = G whole curves (W = G T points)
+  const int Wp = W / G;                   // points of one curve in a window
   constexpr bool F16 = FMT != FMT_TF32;   // fp16 operands (one or two terms)
   constexpr bool X3 = FMT == FMT_F16X3;   // 3-term split
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int M = p.M, K = p.K, T = p.T, n_poly = p.n_poly, Kb = p.Kb;
-  TcSmem s = tc_carve(smem_raw, W, K, M, xl2);
-  const int WSEG = W - 1;  // segments per window
+  TcSmem s = tc_carve<GM>(smem_raw, W, K, M, !xl2);
+  const int WSEG = Wp - 1;  // segments of one curve per window
   uint64_t* full = s.bars;                       // [2][MAX_STAGES]
   uint64_t* empty = s.bars + 2 * MAX_STAGES;     // [2][MAX_STAGES]
   uint64_t* a_ready = s.bars + 4 * MAX_STAGES;
@@ -326,7 +353,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
   unsigned int* queue = reinterpret_cast<unsigned int*>(p.workspace);
   const int unit_steps = p.unit_steps;
   const int nchunks = (p.steps + unit_steps - 1) / unit_steps;
-  const unsigned int total_units = unsigned(p.N) * unsigned(nchunks);
+  const unsigned int ngroups = unsigned((p.N + G - 1) / G);   // work unit = (group of G consecutive curves, chunk of steps)
+  const unsigned int total_units = ngroups * unsigned(nchunks);
 
   if (tid == 0) {
     for (int i = 0; i < 2 * MAX_STAGES; ++i) {
@@ -369,7 +397,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
       // dE/dx operand tiles of this CTA in the workspace (see the epilogue)
       const unsigned char* gtiles = reinterpret_cast<const unsigned char*>(
           reinterpret_cast<const uint32_t*>(p.workspace) + tc_queue_words(p.N) + size_t(blockIdx.x) * tc_ws_cta_words(K, M, W) +
-          size_t(K + 16) * 512 + 2 * size_t(M) * W * XD_STRIDE);
+          size_t(tc_max_items(K, M, W)) * 512 + 2 * size_t(M) * W * XD_STRIDE);
       for (long w = 0;; ++w) {
         mbar_wait(win_ready, uint32_t(w & 1));
         const WinCtl* ctl = &s.ctl[w & 1];
@@ -589,22 +617,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
     // this CTA's slice of the L2-resident workspace (tc_ws_cta_words): ReLU masks, both end-point outputs of
     // every segment, and the dE/dx operand tiles one fused pass builds from them for the backward items
     uint32_t* maskws = reinterpret_cast<uint32_t*>(p.workspace) + tc_queue_words(p.N) + size_t(blockIdx.x) * tc_ws_cta_words(K, M, W);
-    float* X1g = reinterpret_cast<float*>(maskws + size_t(K + 16) * 512);
+    float* X1g = reinterpret_cast<float*>(maskws + size_t(tc_max_items(K, M, W)) * 512);
     float* X1 = xl2 ? X1g : s.XD;   // left-end outputs, then the differences: shared memory when they fit
     float* X2 = X1g + size_t(M) * W * XD_STRIDE;
     unsigned char* Gt = reinterpret_cast<unsigned char*>(X2 + size_t(M) * W * XD_STRIDE);
 
     for (int i = t512; i < 4 * n_poly * Kb; i += EPI_THREADS) s.basis[i] = p.basis[i];
+    const int nchunk = tc_chunks(W);            // the window's points in chunks of 512 (thread = point)
+    const int wpos = t512 >> 5;                 // position of this warp's 32 points inside a chunk
 
     for (;;) {
-      // ---- next work unit: (curve n, steps [step_lo, step_hi)) ----
+      // ---- next work unit: (group of G curves n0 .. n0 + Gcur - 1, steps [step_lo, step_hi)) ----
       if (t512 == 0) {
         const unsigned int u = atomicAdd(&queue[0], 1u);
         s.tmem_base[1] = u;
-        if (u < total_units && u >= unsigned(p.N)) {
-          // a later chunk of a curve: wait until its previous chunk has been written back
-          const unsigned int* flag = &queue[64 + u % unsigned(p.N)];
-          const unsigned int need = u / unsigned(p.N);
+        if (u < total_units && u >= ngroups) {
+          // a later chunk of a group: wait until its previous chunk has been written back
+          const unsigned int* flag = &queue[64 + u % ngroups];
+          const unsigned int need = u / ngroups;
           unsigned int have;
           do {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(have) : "l"(flag) : "memory");
@@ -615,19 +645,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
       named_bar(3, EPI_THREADS);
       const unsigned int unit = s.tmem_base[1];
       if (unit >= total_units) break;
-      const int n = int(unit % unsigned(p.N));
-      const int chunk = int(unit / unsigned(p.N));
+      const int grp = int(unit % ngroups);
+      const int n0 = grp * G, Gcur = min(G, p.N - n0);
+      const int chunk = int(unit / ngroups);
       const int step_lo = chunk * unit_steps, step_hi = min(p.steps, step_lo + unit_steps);
-      if (t512 < 2 * Kb) {
-        s.om[t512] = __ldcg(p.omega + size_t(n) * 2 * Kb + t512);
-        if (GRAD) {
-          s.om[2 * MAX_KB + t512] = __ldcg(p.adam_m + size_t(n) * 2 * Kb + t512);
-          s.om[4 * MAX_KB + t512] = __ldcg(p.adam_v + size_t(n) * 2 * Kb + t512);
+      if (t512 < G * 2 * Kb) {
+        const int j = t512 / (2 * Kb), c = t512 - j * 2 * Kb;
+        if (j < Gcur) {
+          const size_t o = size_t(n0 + j) * 2 * Kb + c;
+          s.om[j * OM_STRIDE + c] = __ldcg(p.omega + o);
+          if (GRAD) {
+            s.om[j * OM_STRIDE + 2 * MAX_KB + c] = __ldcg(p.adam_m + o);
+            s.om[j * OM_STRIDE + 4 * MAX_KB + c] = __ldcg(p.adam_v + o);
+          }
+        } else {
+          s.om[j * OM_STRIDE + c] = 0.f;
         }
       }
-      const float2 pa = make_float2(p.a[2 * n], p.a[2 * n + 1]);
-      const float2 pb = make_float2(p.b[2 * n], p.b[2 * n + 1]);
-      int dec_base = p.dec_base ? p.dec_base[n] : 0;
+      if (t512 < 4 * G) {
+        const int j = t512 >> 2, c = t512 & 3, n = n0 + min(j, Gcur - 1);
+        s.pab[t512] = c < 2 ? p.a[2 * n + c] : p.b[2 * n + c - 2];
+      }
+      // one weight set per window: per-curve sets (decoder_base) are only launched with G = 1
+      int dec_base = p.dec_base ? p.dec_base[n0] : 0;
       if (dec_base < 0 || dec_base + K > p.K_total) {   // memory safety; reported through the status word
         dec_base = 0;
         if (t512 == 0) atomicOr(&queue[1], unsigned(VLG_STATUS_BAD_PACKED));
@@ -635,39 +675,43 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
       named_bar(3, EPI_THREADS);
 
       for (int step = step_lo; step < step_hi; ++step) {
-        if (t512 < 8 * n_poly) {
-          const int r = t512 >> 1, d = t512 & 1;
+        for (int idx = t512; idx < G * 8 * n_poly; idx += EPI_THREADS) {
+          const int j = idx / (8 * n_poly), q = idx - j * 8 * n_poly;
+          const int r = q >> 1, d = q & 1;
           float acc = 0.f;
-          for (int k = 0; k < Kb; ++k) acc = fmaf(s.basis[r * Kb + k], s.om[2 * k + d], acc);
-          s.coef[t512] = acc;
+          for (int k = 0; k < Kb; ++k) acc = fmaf(s.basis[r * Kb + k], s.om[j * OM_STRIDE + 2 * k + d], acc);
+          s.coef[j * 64 + q] = acc;
         }
-        if (t512 < 2 * MAX_KB) s.gacc[t512] = 0.f;
-        float e_tot = 0.f, l_tot = 0.f;  // meaningful in t512 == 0
+        if (t512 < G * 20) s.gacc[t512] = 0.f;
+        if (t512 < G * 2) s.etot[t512] = 0.f;
         named_bar(3, EPI_THREADS);
 
         for (int win = 0; win < nwin; ++win, ++wcount) {
           const int seg0 = win * WSEG;
-          const int nseg = min(WSEG, T - 1 - seg0);
+          const int nseg = min(WSEG, T - 1 - seg0);   // segments of every curve in this window
           WinCtl* ctl = &s.ctl[wcount & 1];
-          // ---- window setup: points, draws, accumulators ----
-          if (t512 < W) {
-            const int pt = t512;
-            const int ti = min(seg0 + pt, T - 1);
-            s.zs[pt] = spline_point(p.t[ti], n_poly, s.coef, pa, pb);
+          // ---- window setup: points, draws, accumulators (point pt = curve j = pt / Wp, local index i) ----
+          for (int pt = t512; pt < W; pt += EPI_THREADS) {
+            const int j = pt / Wp, i = pt - j * Wp;
+            const int ti = min(seg0 + i, T - 1);
+            const float* ab = s.pab + 4 * j;
+            s.zs[pt] = spline_point(p.t[ti], n_poly, s.coef + j * 64, make_float2(ab[0], ab[1]), make_float2(ab[2], ab[3]));
+            const bool seg_ok = i < nseg && j < Gcur;
+            const int n = n0 + j;
             if (p.draws != nullptr) {
               for (int m = 0; m < M; ++m)
                 for (int role = 0; role < 2; ++role) {
                   uint8_t v = 255;
-                  if (pt < nseg) {
-                    v = p.draws[(((size_t(n) * p.steps + step) * M + m) * 2 + role) * size_t(T - 1) + seg0 + pt];
+                  if (seg_ok) {
+                    v = p.draws[(((size_t(n) * p.steps + step) * M + m) * 2 + role) * size_t(T - 1) + seg0 + i];
                     if (v >= K) { v = uint8_t(K - 1); bad_draw = true; }   // memory safety; reported through the status word
                   }
                   s.sel[(m * 2 + role) * W + pt] = v;
                 }
             } else {
               uint32_t d[4] = {255u, 255u, 255u, 255u};
-              if (pt < nseg)
-                counter_draws4(p.seed, uint32_t(p.curve_id0 + n), uint32_t(p.step0 + step), uint32_t(seg0 + pt), 0u,
+              if (seg_ok)
+                counter_draws4(p.seed, uint32_t(p.curve_id0 + n), uint32_t(p.step0 + step), uint32_t(seg0 + i), 0u,
                                uint32_t(K), d);
               for (int q = 0; q < 4; ++q) {
                 const int m = q >> 1;
@@ -676,27 +720,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
             }
           }
           for (int i = t512; i < 4 * W; i += EPI_THREADS) s.dzs[i] = make_float2(0.f, 0.f);
-          if (t512 < K) s.cnt[t512] = 0;
           named_bar(3, EPI_THREADS);
           // ---- per-decoder row lists, in increasing point order ----
           // Item membership must not depend on thread timing: a decoder drawn by more than 128 points of
           // the window is split into several items, which run on different chains, and the chains' dz
           // partial sums are added in a fixed order -- so WHICH points share an item fixes the fp32
-          // summation grouping.  Ordered compaction: thread = point, each warp owns 32 consecutive
-          // points; per decoder a ballot gives the rank inside the warp, a scan over the 16 warps the
-          // warp's base.  (Bit-identical results for any sharding / scheduling of the curves.)
-          {
-            const int pt = t512;
-            const int wpos = t512 >> 5;            // position of this warp's 32 points in the window
-            int cand[2 * TC_MAX_M], rk[2 * TC_MAX_M];
+          // summation grouping.  Ordered compaction: thread = point (chunks of 512 points), each warp owns
+          // 32 consecutive points; per decoder a ballot gives the rank inside the warp, a scan over
+          // (chunk, warp) the warp's base, a scan over the decoders each list's offset.  Two passes over
+          // the ballots: count, then place.  (Bit-identical results for any sharding / scheduling.)
+          const uint32_t lt = (1u << lane) - 1u;
+          auto candidates = [&](int pt, int (&cand)[2 * TC_MAX_M]) {
 #pragma unroll
-            for (int i = 0; i < 2 * TC_MAX_M; ++i) { cand[i] = -1; rk[i] = 0; }
-            if (pt <= nseg) {
+            for (int i = 0; i < 2 * TC_MAX_M; ++i) cand[i] = -1;
+            if (pt < W) {
 #pragma unroll
               for (int m = 0; m < TC_MAX_M; ++m)
                 if (m < M) {
-                  if (pt < nseg) cand[2 * m] = s.sel[(m * 2 + 0) * W + pt];
-                  if (pt >= 1) cand[2 * m + 1] = s.sel[(m * 2 + 1) * W + pt - 1];
+                  const int c0 = s.sel[(m * 2 + 0) * W + pt];                    // left end of its segment
+                  const int c1 = pt >= 1 ? int(s.sel[(m * 2 + 1) * W + pt - 1]) : 255;  // right end of the previous one
+                  if (c0 != 255) cand[2 * m] = c0;
+                  if (c1 != 255) cand[2 * m + 1] = c1;
                 }
 #pragma unroll
               for (int i = 1; i < 2 * TC_MAX_M; ++i)
@@ -704,43 +748,53 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                 for (int j = 0; j < i; ++j)
                   if (cand[j] == cand[i]) cand[i] = -1;   // a point enters a decoder's list once
             }
-            const uint32_t lt = (1u << lane) - 1u;
+          };
+          for (int ch = 0; ch < nchunk; ++ch) {
+            int cand[2 * TC_MAX_M];
+            candidates(ch * 512 + t512, cand);
             for (int k = 0; k < K; ++k) {
               const bool mem = (cand[0] == k) | (cand[1] == k) | (cand[2] == k) | (cand[3] == k);
               const uint32_t bal = __ballot_sync(0xffffffffu, mem);
-              const int r = __popc(bal & lt);
-#pragma unroll
-              for (int i = 0; i < 2 * TC_MAX_M; ++i)
-                if (cand[i] == k) rk[i] = r;
-              if (lane == 0) s.wcnt[k * 16 + wpos] = uint16_t(__popc(bal));
+              if (lane == 0) s.wcnt[(k * nchunk + ch) * 16 + wpos] = uint16_t(__popc(bal));
             }
-            named_bar(3, EPI_THREADS);
-            if (t512 < K) {
-              int acc = 0;
-              for (int w = 0; w < 16; ++w) {
-                const int c = s.wcnt[t512 * 16 + w];
-                s.wcnt[t512 * 16 + w] = uint16_t(acc);
-                acc += c;
-              }
-              s.cnt[t512] = acc;
-            }
-            named_bar(3, EPI_THREADS);
-#pragma unroll
-            for (int i = 0; i < 2 * TC_MAX_M; ++i)
-              if (cand[i] >= 0) s.rows[cand[i] * W + s.wcnt[cand[i] * 16 + wpos] + rk[i]] = uint16_t(pt);
           }
+          named_bar(3, EPI_THREADS);
+          if (t512 < K) {
+            int acc = 0;
+            for (int w = 0; w < nchunk * 16; ++w) {
+              const int c = s.wcnt[t512 * nchunk * 16 + w];
+              s.wcnt[t512 * nchunk * 16 + w] = uint16_t(acc);
+              acc += c;
+            }
+            s.cnt[t512] = acc;
+          }
+          named_bar(3, EPI_THREADS);
           if (t512 == 0) {
             // the control warps must be done with the item list this one replaces (window wcount - 2)
             if (wcount >= 2) mbar_wait(&ctl_free[wcount & 1], uint32_t(((wcount >> 1) - 1) & 1));
-            int ni = 0;
-            for (int k = 0; k < K; ++k)
+            int ni = 0, off = 0;
+            for (int k = 0; k < K; ++k) {
+              s.roff[k] = off;
+              off += s.cnt[k];
               for (int q = 0; q * 128 < s.cnt[k]; ++q) ctl->item[ni++] = uint16_t(k | (q << 8));
+            }
             ctl->nitems = ni;
             ctl->base = dec_base;
             n_items += unsigned(ni);
-            for (int k = 0; k < K; ++k) n_rows += unsigned(s.cnt[k]);
+            n_rows += unsigned(off);
             __threadfence_block();
             mbar_arrive(win_ready);
+          }
+          named_bar(3, EPI_THREADS);
+          for (int ch = 0; ch < nchunk; ++ch) {
+            int cand[2 * TC_MAX_M];
+            const int pt = ch * 512 + t512;
+            candidates(pt, cand);
+            for (int k = 0; k < K; ++k) {
+              const bool mem = (cand[0] == k) | (cand[1] == k) | (cand[2] == k) | (cand[3] == k);
+              const uint32_t bal = __ballot_sync(0xffffffffu, mem);
+              if (mem) s.rows[s.roff[k] + s.wcnt[(k * nchunk + ch) * 16 + wpos] + __popc(bal & lt)] = uint16_t(pt);
+            }
           }
           named_bar(3, EPI_THREADS);
           const int nitems = ctl->nitems;
@@ -751,7 +805,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
             // tcgen05.ld/st are warp-collective (.sync.aligned): a warp takes part as soon as one of
             // its 32 rows is in use; unused lanes compute on point 0 and store nothing
             const bool wact = q0 + (warp & 3) * 32 < s.cnt[k];
-            const int pt = active ? s.rows[k * W + q0 + row] : 0;
+            const int pt = active ? s.rows[s.roff[k] + q0 + row] : 0;
             // small weights of decoder k: loaded by the chain's producer (bulk copy -> mbarrier).  TF32
             // operands overwrite accumulators in place, so the group must also be done with the previous
             // item's D3 before layer 1 is stored; fp16 operands and accumulators never share columns.
@@ -910,33 +964,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
             // 16-byte pieces (x2 from the workspace, x1 from shared memory or the workspace, the difference back in
             // place of x1), four independent pieces per thread in flight.  The energy is the plain sum of squares,
             // in a fixed order (deterministic).
-            float e = 0.f;
             const int n4 = nseg * (XD_STRIDE / 4);
-            for (int m = 0; m < M; ++m) {
-              const float4* x2 = reinterpret_cast<const float4*>(X2 + m * W * XD_STRIDE);
-              float4* x1 = reinterpret_cast<float4*>(X1 + m * W * XD_STRIDE);
-              for (int i0 = t512; i0 < n4; i0 += 4 * EPI_THREADS) {
-                float4 v[4], u[4];
+            for (int jc = 0; jc < Gcur; ++jc) {      // the segments of one curve are contiguous rows: its energy
+              float e = 0.f;
+              for (int m = 0; m < M; ++m) {
+                const float4* x2 = reinterpret_cast<const float4*>(X2 + size_t(m * W + jc * Wp) * XD_STRIDE);
+                float4* x1 = reinterpret_cast<float4*>(X1 + size_t(m * W + jc * Wp) * XD_STRIDE);
+                for (int i0 = t512; i0 < n4; i0 += 4 * EPI_THREADS) {
+                  float4 v[4], u[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const int i = i0 + j * EPI_THREADS;
-                  v[j] = i < n4 ? __ldcg(x2 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-                  if (xl2) u[j] = i < n4 ? __ldcg(x1 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
+                  for (int j = 0; j < 4; ++j) {
+                    const int i = i0 + j * EPI_THREADS;
+                    v[j] = i < n4 ? __ldcg(x2 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (xl2) u[j] = i < n4 ? __ldcg(x1 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                  }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const int i = i0 + j * EPI_THREADS;
-                  if (i < n4) {
-                    if (!xl2) u[j] = x1[i];
-                    const float4 a = make_float4(v[j].x - u[j].x, v[j].y - u[j].y, v[j].z - u[j].z, v[j].w - u[j].w);
-                    x1[i] = a;
-                    e = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(a.z, a.z, fmaf(a.w, a.w, e))));
+                  for (int j = 0; j < 4; ++j) {
+                    const int i = i0 + j * EPI_THREADS;
+                    if (i < n4) {
+                      if (!xl2) u[j] = x1[i];
+                      const float4 a = make_float4(v[j].x - u[j].x, v[j].y - u[j].y, v[j].z - u[j].z, v[j].w - u[j].w);
+                      x1[i] = a;
+                      e = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(a.z, a.z, fmaf(a.w, a.w, e))));
+                    }
                   }
                 }
               }
+              e = warp_sum(e);
+              if (lane == 0) s.red[320 + jc * 32 + ew] = e;
             }
-            e = warp_sum(e);
-            if (lane == 0) s.red[320 + ew] = e;
             named_bar(3, EPI_THREADS);  // the differences are read by other threads below
             // (2) [only when the differences live in the workspace, xl2: from shared memory the backward items build
             // their dE/dx rows themselves -- inside an item the other chain hides the latency, a CTA-wide pass cannot;
@@ -951,7 +1007,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
               const int it = t0 >> 10, c = (t0 >> 7) & 7, r = t0 & 127;
               const int k = ctl->item[it] & 0xFF, q0 = (ctl->item[it] >> 8) * 128;
               if (q0 + r >= s.cnt[k]) continue;
-              const int pt = s.rows[k * W + q0 + r];
+              const int pt = s.rows[s.roff[k] + q0 + r];
               float g[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) g[j] = 0.f;
@@ -1014,38 +1070,42 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
           } else {
             // forward-only kernel (also reports the polyline length, a sum of per-segment norms): 16 lanes
             // per (m, segment) entry, one 16-byte piece each; six entries per lane in flight.
-            float e = 0.f, l = 0.f;
             const int sub = lane & 15;
             constexpr int NV = XD_STRIDE / 4;   // 13 float4 per row
             constexpr int UNR = 6;
-            const int nent = M * W;
-            for (int base = ew * 2 + (lane >> 4); base < nent; base += 32 * UNR) {
-              float4 v[UNR];
+            const int nent = M * Wp;            // (m, local point) entries of one curve
+            for (int jc = 0; jc < Gcur; ++jc) {
+              float e = 0.f, l = 0.f;
+              for (int base = ew * 2 + (lane >> 4); base < nent; base += 32 * UNR) {
+                float4 v[UNR];
 #pragma unroll
-              for (int j = 0; j < UNR; ++j) {
-                const int ent = base + 32 * j;
-                const bool ok = ent < nent && (ent % W) < nseg && sub < NV;
-                v[j] = ok ? __ldcg(reinterpret_cast<const float4*>(X2 + ent * XD_STRIDE) + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
-              }
-#pragma unroll
-              for (int j = 0; j < UNR; ++j) {
-                const int ent = base + 32 * j;
-                const bool ok = ent < nent && (ent % W) < nseg && sub < NV;
-                float q = 0.f;
-                if (ok) {
-                  const float4* up = reinterpret_cast<const float4*>(X1 + ent * XD_STRIDE) + sub;
-                  const float4 u = xl2 ? __ldcg(up) : *up;
-                  const float4 a = make_float4(v[j].x - u.x, v[j].y - u.y, v[j].z - u.z, v[j].w - u.w);
-                  q = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(a.z, a.z, a.w * a.w)));
+                for (int j = 0; j < UNR; ++j) {
+                  const int ent = base + 32 * j;
+                  const bool ok = ent < nent && (ent % Wp) < nseg && sub < NV;
+                  const size_t r_ = size_t((ent / Wp) * W + jc * Wp + (ent % Wp)) * XD_STRIDE;
+                  v[j] = ok ? __ldcg(reinterpret_cast<const float4*>(X2 + r_) + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
 #pragma unroll
-                for (int o = 8; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-                if (sub == 0) { e += q; l += sqrtf(q); }
+                for (int j = 0; j < UNR; ++j) {
+                  const int ent = base + 32 * j;
+                  const bool ok = ent < nent && (ent % Wp) < nseg && sub < NV;
+                  float q = 0.f;
+                  if (ok) {
+                    const size_t r_ = size_t((ent / Wp) * W + jc * Wp + (ent % Wp)) * XD_STRIDE;
+                    const float4* up = reinterpret_cast<const float4*>(X1 + r_) + sub;
+                    const float4 u = xl2 ? __ldcg(up) : *up;
+                    const float4 a = make_float4(v[j].x - u.x, v[j].y - u.y, v[j].z - u.z, v[j].w - u.w);
+                    q = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(a.z, a.z, a.w * a.w)));
+                  }
+#pragma unroll
+                  for (int o = 8; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+                  if (sub == 0) { e += q; l += sqrtf(q); }
+                }
               }
+              e = warp_sum(e);
+              l = warp_sum(l);
+              if (lane == 0) { s.red[320 + jc * 32 + ew] = e; s.red[320 + jc * 32 + 16 + ew] = l; }
             }
-            e = warp_sum(e);
-            l = warp_sum(l);
-            if (lane == 0) { s.red[320 + ew] = e; s.red[336 + ew] = l; }
           }
           if (GRAD) {
             named_bar(3, EPI_THREADS);            // every tile of the window is written (and fenced for the async proxy)
@@ -1054,11 +1114,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
 
           if (GRAD) {
             // =============================== backward ===============================
+            // dz of a (point, decoder) row = sum of its two half-threads' partials; it goes to the cell of the FIRST draw
+            // slot of the point that holds this decoder -- each cell is written exactly once, and the <= 4 cells of a
+            // point are added in slot order afterwards: the result does not depend on which item / chain / window-mate
+            // a row was processed with.  The halves meet through dzx one item later (the chain's next MMA round trip
+            // is a barrier between the group's threads).
+            int pend_pt = -1, pend_slot = 0;
             for (int it = chain_id; it < nitems; it += 2) {
               const int k = ctl->item[it] & 0xFF, q0 = (ctl->item[it] >> 8) * 128;
               const bool active = q0 + row < s.cnt[k];
               const bool wact = q0 + (warp & 3) * 32 < s.cnt[k];
-              const int pt = active ? s.rows[k * W + q0 + row] : 0;
+              const int pt = active ? s.rows[s.roff[k] + q0 + row] : 0;
               mbar_wait(&sw_full[chain_id * SW_SLOTS + (swj % SW_SLOTS)], (swj / SW_SLOTS) & 1u);
               if (!F16) named_bar(bar_id, GROUP_THREADS);
               const float* sw = swbuf + (swj % SW_SLOTS) * 576;
@@ -1127,6 +1193,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
               { STAT_T0(); acc_wait(&acc_ready[chain_id], ph_acc, lane); STAT_ADD(w_acc); }
               ph_acc ^= 1;
               tc_fence_after();
+              if (half == 0 && pend_pt >= 0) {   // the previous item's row: both halves are in dzx now
+                const float2 u0 = s.dzx[(chain_id * 2 + 0) * 128 + row], u1 = s.dzx[(chain_id * 2 + 1) * 128 + row];
+                s.dzs[pend_slot * W + pend_pt] = make_float2(u0.x + u1.x, u0.y + u1.y);
+              }
               if (wact) {
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
@@ -1184,96 +1254,115 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                     ay = __ffma2_rn(dh, wy, ay);
                   }
                 }
-                // a point occurs at most once per item and the items of a chain run in order:
-                // plain read-modify-write, deterministic
                 if (active) {
-                  float2* dzp = &s.dzs[(chain_id * 2 + half) * W + pt];
-                  float2 acc = *dzp;
                   constexpr float unscale = F16 ? 1.f / F16_GRAD_SCALE : 1.f;
-                  acc.x += (ax.x + ax.y) * unscale;
-                  acc.y += (ay.x + ay.y) * unscale;
-                  *dzp = acc;
+                  s.dzx[(chain_id * 2 + half) * 128 + row] = make_float2((ax.x + ax.y) * unscale, (ay.x + ay.y) * unscale);
                 }
               }
-            }
-          }
-          named_bar(3, EPI_THREADS);
-          // ---- d(omega) += P^T dz over the points of the window, energy partials ----
-          if (GRAD) {
-            // all 512 epilogue threads, one point each (W <= 512); threads beyond the window add zeros
-            const int pt = t512;
-            float P[MAX_KB];
-            float dx = 0.f, dy = 0.f;
-            if (pt < W) {
-              design_row(p.t[min(seg0 + pt, T - 1)], n_poly, Kb, s.basis, P);
-              const float2 d0 = s.dzs[pt], d1 = s.dzs[W + pt], d2 = s.dzs[2 * W + pt], d3 = s.dzs[3 * W + pt];
-              dx = (d0.x + d1.x) + (d2.x + d3.x);
-              dy = (d0.y + d1.y) + (d2.y + d3.y);
-            } else {
-#pragma unroll
-              for (int k = 0; k < MAX_KB; ++k) P[k] = 0.f;
-            }
-#pragma unroll
-            for (int k = 0; k < MAX_KB; ++k)
-              if (k < Kb) {
-                const float cx = warp_sum(P[k] * dx), cy = warp_sum(P[k] * dy);
-                if (lane == 0) { s.red[ew * 20 + 2 * k] = cx; s.red[ew * 20 + 2 * k + 1] = cy; }
+              pend_pt = -1;
+              if (active && half == 0) {
+                pend_pt = pt;
+                pend_slot = s.sel[pt] == k ? 0 : (pt >= 1 && s.sel[W + pt - 1] == k) ? 1 : (M > 1 && s.sel[2 * W + pt] == k) ? 2 : 3;
               }
-          }
-          if (t512 == 0) {
-            float ee = 0.f, ll = 0.f;
-            for (int w = 0; w < 16; ++w) { ee += s.red[320 + w]; ll += s.red[336 + w]; }
-            e_tot += ee;
-            l_tot += ll;
+            }
+            named_bar(3, EPI_THREADS);
+            if (half == 0 && pend_pt >= 0) {     // the last item of each chain
+              const float2 u0 = s.dzx[(chain_id * 2 + 0) * 128 + row], u1 = s.dzx[(chain_id * 2 + 1) * 128 + row];
+              s.dzs[pend_slot * W + pend_pt] = make_float2(u0.x + u1.x, u0.y + u1.y);
+            }
           }
           named_bar(3, EPI_THREADS);
-          if (GRAD && t512 < 2 * Kb) {
-            float g = 0.f;
-            for (int w = 0; w < 16; ++w) g += s.red[w * 20 + t512];
-            s.gacc[t512] += g;
+          // ---- energy of the window per curve; d(omega) += P^T dz over the points of the window ----
+          if (t512 < Gcur) {
+            float ee = 0.f, ll = 0.f;
+            for (int w = 0; w < 16; ++w) { ee += s.red[320 + t512 * 32 + w]; ll += s.red[320 + t512 * 32 + 16 + w]; }
+            s.etot[2 * t512] += ee;
+            if (!GRAD) s.etot[2 * t512 + 1] += ll;
+          }
+          if (GRAD) {
+            // chunks of 512 points, one point per thread; a warp's 32 points belong to one curve (Wp % 32 == 0
+            // whenever a window holds several curves); per chunk the 16 warp partials are added to their curves'
+            // gradients in warp order by one thread per coefficient (fixed order)
+            for (int ch = 0; ch < nchunk; ++ch) {
+              const int pt = ch * 512 + t512;
+              float P[MAX_KB];
+              float dx = 0.f, dy = 0.f;
+              if (pt < W) {
+                const int i = pt - (pt / Wp) * Wp;
+                design_row(p.t[min(seg0 + i, T - 1)], n_poly, Kb, s.basis, P);
+                const float2 d0 = s.dzs[pt], d1 = s.dzs[W + pt], d2 = s.dzs[2 * W + pt], d3 = s.dzs[3 * W + pt];
+                dx = (d0.x + d1.x) + (d2.x + d3.x);
+                dy = (d0.y + d1.y) + (d2.y + d3.y);
+              } else {
+#pragma unroll
+                for (int k = 0; k < MAX_KB; ++k) P[k] = 0.f;
+              }
+#pragma unroll
+              for (int k = 0; k < MAX_KB; ++k)
+                if (k < Kb) {
+                  const float cx = warp_sum(P[k] * dx), cy = warp_sum(P[k] * dy);
+                  if (lane == 0) { s.red[wpos * 20 + 2 * k] = cx; s.red[wpos * 20 + 2 * k + 1] = cy; }
+                }
+              named_bar(3, EPI_THREADS);
+              if (t512 < 2 * Kb) {
+                for (int w = 0; w < 16; ++w) {
+                  const int p0 = ch * 512 + w * 32;
+                  if (p0 < W) s.gacc[(p0 / Wp) * 20 + t512] += s.red[w * 20 + t512];
+                }
+              }
+              named_bar(3, EPI_THREADS);
+            }
+          } else {
+            named_bar(3, EPI_THREADS);
           }
         }  // windows
 
-        named_bar(3, EPI_THREADS);
-        if (t512 == 0) {
-          const float E = e_tot / float(M);
+        if (t512 < Gcur) {
+          const int n = n0 + t512;
+          const float E = s.etot[2 * t512] / float(M);
           // fp16 operands overflow above 65504: inf/NaN reach the energy (forward) or omega (backward)
           if (!(fabsf(E) <= 3.0e38f)) atomicOr(&queue[1], unsigned(VLG_STATUS_NONFINITE));
           if (p.energy_trace) p.energy_trace[size_t(step) * p.N + n] = E;
           if (step == p.steps - 1) {
             if (p.energy_last) p.energy_last[n] = E;
-            if (p.length_out) p.length_out[n] = l_tot / float(M);
+            if (p.length_out) p.length_out[n] = s.etot[2 * t512 + 1] / float(M);
           }
         }
-        if (GRAD && t512 < 2 * Kb) {
-          const int k = t512 >> 1, d = t512 & 1;
+        if (GRAD && t512 < Gcur * 2 * Kb) {
+          const int j = t512 / (2 * Kb), c = t512 - j * 2 * Kb;
+          const int k = c >> 1, d = c & 1;
           const float tend = p.t[T - 1];
           float P[MAX_KB];
           design_row(tend, n_poly, Kb, s.basis, P);
-          const float2 ze = spline_point(tend, n_poly, s.coef, pa, pb);
+          const float* ab = s.pab + 4 * j;
+          const float2 pb = make_float2(ab[2], ab[3]);
+          const float2 ze = spline_point(tend, n_poly, s.coef + j * 64, make_float2(ab[0], ab[1]), pb);
           const float err = d == 0 ? ze.x - pb.x : ze.y - pb.y;
-          const float g = s.gacc[t512] + (2.0f * p.penalty_w) * err * P[k];
+          const float g = s.gacc[j * 20 + c] + (2.0f * p.penalty_w) * err * P[k];
           AdamScalars sc = adam_scalars(p.step0 + step + 1, p.lr, p.beta1, p.beta2);
-          float om = s.om[t512], mm = s.om[2 * MAX_KB + t512], vv = s.om[4 * MAX_KB + t512];
+          float* o = s.om + j * OM_STRIDE;
+          float om = o[c], mm = o[2 * MAX_KB + c], vv = o[4 * MAX_KB + c];
           adam_update(om, mm, vv, g, sc, p.one_minus_b1, p.beta2f, p.one_minus_b2, p.eps);
-          s.om[t512] = om;
-          s.om[2 * MAX_KB + t512] = mm;
-          s.om[4 * MAX_KB + t512] = vv;
+          o[c] = om;
+          o[2 * MAX_KB + c] = mm;
+          o[4 * MAX_KB + c] = vv;
         }
         named_bar(3, EPI_THREADS);
       }  // steps
 
-      if (GRAD && t512 < 2 * Kb) {
-        p.omega[size_t(n) * 2 * Kb + t512] = s.om[t512];
-        p.adam_m[size_t(n) * 2 * Kb + t512] = s.om[2 * MAX_KB + t512];
-        p.adam_v[size_t(n) * 2 * Kb + t512] = s.om[4 * MAX_KB + t512];
-        if (!(fabsf(s.om[t512]) <= 3.0e38f)) atomicOr(&queue[1], unsigned(VLG_STATUS_NONFINITE));
+      if (GRAD && t512 < Gcur * 2 * Kb) {
+        const int j = t512 / (2 * Kb), c = t512 - j * 2 * Kb;
+        const size_t o = size_t(n0 + j) * 2 * Kb + c;
+        p.omega[o] = s.om[j * OM_STRIDE + c];
+        p.adam_m[o] = s.om[j * OM_STRIDE + 2 * MAX_KB + c];
+        p.adam_v[o] = s.om[j * OM_STRIDE + 4 * MAX_KB + c];
+        if (!(fabsf(s.om[j * OM_STRIDE + c]) <= 3.0e38f)) atomicOr(&queue[1], unsigned(VLG_STATUS_NONFINITE));
         __threadfence();
       }
       named_bar(3, EPI_THREADS);
       if (t512 == 0) {
         const unsigned int v = unsigned(chunk) + 1u;
-        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&queue[64 + n]), "r"(v) : "memory");
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&queue[64 + grp]), "r"(v) : "memory");
       }
     }  // work units
     if (bad_draw) atomicOr(&queue[1], unsigned(VLG_STATUS_BAD_DRAW));
@@ -1317,46 +1406,64 @@ static int tc_grid(int N) {
 // or the L2-resident workspace (xl2 = 1; any window up to TC_MAX_W points, but the dE/dx tile pass then sits on
 // L2 latency: measured +45 % per item on the headline shape).
 struct TcPlan {
-  int W, nst, xl2;
+  int W, nst, xl2, G;   // W = points per window (all curves), G = curves per window
 };
-static TcPlan tc_plan(int T, int K, int M) {
+static double tc_expected_items(int w, double p) {
+  const double mean = w * p, sd = sqrt(w * p * (1.0 - p)) + 1e-9;
+  double items = 0.0;
+  for (int q = 0; q * 128 < w; ++q) items += 0.5 * erfc((q * 128 + 0.5 - mean) / (sd * 1.4142135623730951));  // P(n > 128 q)
+  return items;
+}
+static TcPlan tc_plan(int T, int K, int M, bool allow_multi) {
   const double p = 1.0 - pow(1.0 - 1.0 / K, 2.0 * M);
   const int segs = T - 1;
-  int force_nwin = 0, force_xl2 = -1;
+  int force_nwin = 0, force_xl2 = -1, force_g = 0;
   if (const char* env = getenv("VLG_TC_WINDOW")) force_nwin = atoi(env);   // tuning overrides
   if (const char* env = getenv("VLG_TC_XL2")) force_xl2 = atoi(env);
-  TcPlan best = {0, 0, 0};
+  if (const char* env = getenv("VLG_TC_G")) force_g = atoi(env);
+  TcPlan best = {0, 0, 0, 1};
   double best_cost = 1e300;
   for (int xl2 = 0; xl2 < 2; ++xl2) {
     if (force_xl2 >= 0 && xl2 != force_xl2) continue;
+    // one curve per window, nwin windows along the curve
     for (int nwin = 1; nwin <= segs; ++nwin) {
       const int w = (segs + nwin - 1) / nwin + 1;  // points per window
       if (force_nwin >= 1 && nwin != force_nwin) {
         if (w <= 128) break;
         continue;
       }
-      if (w <= TC_MAX_W) {
+      if (w <= TC_MAX_W && force_g <= 1) {
         const int nst = tc_stages(w, K, M, xl2);
         if (nst >= 2) {
-          const double mean = w * p, sd = sqrt(w * p * (1.0 - p)) + 1e-9;
-          double items = 0.0;
-          for (int q = 0; q * 128 < w; ++q) items += 0.5 * erfc((q * 128 + 0.5 - mean) / (sd * 1.4142135623730951));  // P(n > 128 q)
-          double cost = nwin * (K * items + 0.35);  // + per-window fixed cost in item units
+          double cost = nwin * (K * tc_expected_items(w, p) + 0.35);  // + per-window fixed cost in item units
           if (nst == 2) cost *= 1.04;               // a two-stage weight ring cannot hold a whole GEMM's weights
           if (xl2) cost *= 1.45;
-          if (cost < best_cost) { best_cost = cost; best = {w, nst, xl2}; }
+          if (cost < best_cost) { best_cost = cost; best = {w, nst, xl2, 1}; }
         }
       }
       if (w <= 128) break;
     }
+    // G whole curves per window (short curves, many decoders: one curve alone leaves the 128-row items almost empty)
+    if (xl2 && allow_multi && T % 32 == 0)
+      for (int g = 2; g <= TC_MAX_G && g * T <= TC_MAX_WG; ++g) {
+        if (force_g >= 2 && g != force_g) continue;
+        const int w = g * T;
+        const int nst = tc_stages(w, K, M, 1);
+        if (nst < 2) continue;
+        double cost = (K * tc_expected_items(w, p) + 0.35) / g * 1.45;
+        if (nst == 2) cost *= 1.04;
+        if (cost < best_cost) { best_cost = cost; best = {w, nst, 1, g}; }
+      }
   }
   return best;  // W == 0: does not fit
 }
 
 size_t tc_workspace_bytes(int N, int T, int K, int M) {
   if (M > TC_MAX_M || K > TC_MAX_K) return 0;
-  const TcPlan pl = tc_plan(T, K, M);
-  return tc_queue_words(N) * 4 + size_t(tc_grid(N)) * tc_ws_cta_words(K, M, pl.W) * 4;
+  const TcPlan pl = tc_plan(T, K, M, true);   // the multi-curve plan needs at least as much as the single-curve one
+  const TcPlan p1 = tc_plan(T, K, M, false);
+  const size_t a = tc_ws_cta_words(K, M, pl.W), b = tc_ws_cta_words(K, M, p1.W);
+  return tc_queue_words(N) * 4 + size_t(tc_grid(N)) * (a > b ? a : b) * 4;
 }
 
 #ifdef VLG_TC_STATS
@@ -1369,16 +1476,17 @@ cudaError_t launch_tc(const StepParams& p, bool grad, cudaStream_t stream) {
   if (p.precision < 1 || p.precision > 3) return cudaErrorNotSupported;
   const int fmt = p.precision == 1 ? FMT_TF32 : p.precision == 3 ? FMT_F16 : FMT_F16X3;
   if (p.M > TC_MAX_M || p.K > TC_MAX_K) return cudaErrorNotSupported;
-  const TcPlan pl = tc_plan(p.T, p.K, p.M);
-  const int W = pl.W, nst = pl.nst, xl2 = pl.xl2;
+  const TcPlan pl = tc_plan(p.T, p.K, p.M, p.dec_base == nullptr);   // per-curve weight sets: one curve per window
+  const int W = pl.W, nst = pl.nst, xl2 = pl.xl2, G = pl.G;
   if (W < 2 || nst < 2) return cudaErrorNotSupported;
   if (p.workspace == nullptr || p.workspace_bytes < tc_workspace_bytes(p.N, p.T, p.K, p.M)) return cudaErrorInvalidValue;
   const size_t smem = tc_smem_fixed_bytes(W, p.K, p.M, xl2) + size_t(2) * nst * STAGE_BYTES;
-  const int grid = tc_grid(p.N);
+  const int ngroups = (p.N + G - 1) / G;
+  const int grid = tc_grid(ngroups);
   StepParams q = p;
-  // chunks of a curve per launch: at least 4, and enough work units (~48 per CTA) that the last wave's
+  // chunks of a curve (group) per launch: at least 4, and enough work units (~48 per CTA) that the last wave's
   // tail -- at most one unit -- stays a small fraction of the launch
-  int nchunks = (48 * grid + p.N - 1) / p.N;
+  int nchunks = (48 * grid + ngroups - 1) / ngroups;
   if (nchunks < 4) nchunks = 4;
   if (nchunks > q.steps) nchunks = q.steps;
   q.unit_steps = (q.steps + nchunks - 1) / nchunks;
@@ -1387,7 +1495,7 @@ cudaError_t launch_tc(const StepParams& p, bool grad, cudaStream_t stream) {
   auto launch = [&](auto kernel) -> cudaError_t {
     cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (err != cudaSuccess) return err;
-    kernel<<<grid, TC_THREADS, smem, stream>>>(q, nst, W);
+    kernel<<<grid, TC_THREADS, smem, stream>>>(q, nst, W, G);
     return cudaGetLastError();
   };
   auto by_fmt = [&](auto grad_c, auto xl2_c) -> cudaError_t {
