@@ -623,8 +623,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
     unsigned char* Gt = reinterpret_cast<unsigned char*>(X2 + size_t(M) * W * XD_STRIDE);
 
     for (int i = t512; i < 4 * n_poly * Kb; i += EPI_THREADS) s.basis[i] = p.basis[i];
-    const int nchunk = tc_chunks(W);            // the window's points in chunks of 512 (thread = point)
-    const int wpos = t512 >> 5;                 // position of this warp's 32 points inside a chunk
+    const int nchunk = XL2 ? tc_chunks(W) : 1;  // the window's points in chunks of 512 (thread = point)
 
     for (;;) {
       // ---- next work unit: (group of G curves n0 .. n0 + Gcur - 1, steps [step_lo, step_hi)) ----
@@ -646,7 +645,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
       const unsigned int unit = s.tmem_base[1];
       if (unit >= total_units) break;
       const int grp = int(unit % ngroups);
-      const int n0 = grp * G, Gcur = min(G, p.N - n0);
+      const int n0 = grp * G, Gcur = XL2 ? min(G, p.N - n0) : 1;
       const int chunk = int(unit / ngroups);
       const int step_lo = chunk * unit_steps, step_hi = min(p.steps, step_lo + unit_steps);
       if (t512 < G * 2 * Kb) {
@@ -730,6 +729,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
           // (chunk, warp) the warp's base, a scan over the decoders each list's offset.  Two passes over
           // the ballots: count, then place.  (Bit-identical results for any sharding / scheduling.)
           const uint32_t lt = (1u << lane) - 1u;
+          const int wpos = t512 >> 5;                 // position of this warp's 32 points inside a chunk
           auto candidates = [&](int pt, int (&cand)[2 * TC_MAX_M]) {
 #pragma unroll
             for (int i = 0; i < 2 * TC_MAX_M; ++i) cand[i] = -1;
@@ -1283,6 +1283,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
             // chunks of 512 points, one point per thread; a warp's 32 points belong to one curve (Wp % 32 == 0
             // whenever a window holds several curves); per chunk the 16 warp partials are added to their curves'
             // gradients in warp order by one thread per coefficient (fixed order)
+            const int wpos = t512 >> 5;
             for (int ch = 0; ch < nchunk; ++ch) {
               const int pt = ch * 512 + t512;
               float P[MAX_KB];
