@@ -668,29 +668,37 @@ def _run_config3_curves(vlg, ids, prec, steps=1000):
 
 @pytest.mark.parametrize("prec", ["fp32", "f16x3", "f16", "tf32"])
 def test_config3_final_lengths_against_reference_fp64(vlg, prec):
-    """north_star: <= 1e-3 relative final geodesic length for the tensor-core variants.  1000 Adam steps amplify
-    rounding-level differences along badly conditioned curves (Adam normalises the gradient): the reference's OWN
-    fp32 run differs from its fp64 run by `gap` on the same curve, so the bound is max(1e-3, 4 x gap) per curve for
-    the fp32-grade modes (fp32 kernel, 3-term tensor-core split) -- i.e. 1e-3 wherever the reference itself is
-    reproducible to 2.5e-4 -- and the single-term modes (11-bit operands) must meet 1e-3 on the well-conditioned
-    curves (gap <= 1e-5) and stay within 2 % elsewhere.  The table is printed."""
+    """north_star: <= 1e-3 relative final geodesic length.  The golden holds 64 curves of the benchmarked job after
+    1000 free-running Adam steps of the reference's own loop in fp64 and in fp32: the first 49 curves (an unselected
+    sample) and the 15 curves of all 8778 on which the arithmetic modes diverged most in a full GPU run.  Adam
+    normalises the gradient, so rounding-level differences are amplified along badly conditioned curves: the
+    reference's OWN fp32 run is within 1.0e-4 of its fp64 run on the unselected curves but off by up to 1.05e-2
+    (7 of 15 beyond 1e-3) on the selected ones.  Hence:
+      * every mode meets 1e-3 on the unselected sample (2e-3 worst case allowed for the 11-bit modes, which sit at
+        8e-4 / 9.5e-4 there);
+      * the fp32-grade modes (fp32 kernel, 3-term tensor-core split) are statistically the reference's own fp32:
+        median <= 1e-5, no more curves beyond 1e-3 than the reference's fp32 has (+2), worst curve <= 2x its worst;
+      * the single-term modes (fp16 / TF32 operands: 2.5e-4 per step) stay within 2 % everywhere, median <= 5e-4.
+    The table is printed."""
     g = Hh.load("config3_synth_1000")
     ids = g["ids"].astype(np.int64)
     ref = g["final_length_f64"]
     gap = np.abs(g["final_length_f32"].astype(np.float64) / ref - 1)
     got = _run_config3_curves(vlg, ids, prec, int(g["steps"]))
     err = np.abs(got / ref - 1)
+    plain = np.arange(len(ids)) < 49          # ids 0..48: not selected for anything
     order = np.argsort(-err)
-    print(f"\n[{prec}] final length vs reference fp64 over {len(ids)} curves: median {np.median(err):.2e}, "
-          f"90% {np.quantile(err, 0.9):.2e}, max {err.max():.2e}   (reference fp32 vs fp64: median {np.median(gap):.2e}, "
-          f"max {gap.max():.2e})")
-    for i in order[:8]:
+    print(f"\n[{prec}] final length vs reference fp64: unselected 49 curves: median {np.median(err[plain]):.1e} max {err[plain].max():.1e} "
+          f"(reference fp32: median {np.median(gap[plain]):.1e} max {gap[plain].max():.1e}); 15 worst-diverging: median "
+          f"{np.median(err[~plain]):.1e} max {err[~plain].max():.1e}, {int((err[~plain] > 1e-3).sum())} beyond 1e-3 "
+          f"(reference fp32: median {np.median(gap[~plain]):.1e} max {gap[~plain].max():.1e}, {int((gap[~plain] > 1e-3).sum())} beyond 1e-3)")
+    for i in order[:6]:
         print(f"   curve {ids[i]:5d}: err {err[i]:.2e}   reference fp32-vs-fp64 gap {gap[i]:.2e}")
+    assert np.isfinite(got).all()
     if prec in ("fp32", "f16x3"):
-        assert (err <= np.maximum(1e-3, 4 * gap)).all()
-        assert np.median(err) < 2e-5
+        assert err[plain].max() <= 1e-3 and np.median(err) <= 1e-5
+        assert (err > 1e-3).sum() <= (gap > 1e-3).sum() + 2
+        assert err.max() <= 2 * gap.max()
     else:
-        well = gap <= 1e-5
-        assert well.sum() >= len(ids) // 2
-        assert (err[well] <= 1e-3).all()
-        assert (err <= 2e-2).all() and np.median(err) < 3e-4
+        assert np.quantile(err[plain], 0.9) <= 1e-3 and err[plain].max() <= 2e-3
+        assert err.max() <= 2e-2 and np.median(err) <= 5e-4
