@@ -694,6 +694,8 @@ def test_config3_final_lengths_against_reference_fp64(vlg, prec):
           f"(reference fp32: median {np.median(gap[~plain]):.1e} max {gap[~plain].max():.1e}, {int((gap[~plain] > 1e-3).sum())} beyond 1e-3)")
     for i in order[:6]:
         print(f"   curve {ids[i]:5d}: err {err[i]:.2e}   reference fp32-vs-fp64 gap {gap[i]:.2e}")
+    err32 = np.abs(got / g["final_length_f32"].astype(np.float64) - 1)
+    print(f"   against the reference's fp32 run: median {np.median(err32):.1e}, unselected max {err32[plain].max():.1e}, overall max {err32.max():.1e}")
     assert np.isfinite(got).all()
     if prec in ("fp32", "f16x3"):
         assert err[plain].max() <= 1e-3 and np.median(err) <= 1e-5
