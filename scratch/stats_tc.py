@@ -31,12 +31,12 @@ ph = (ctypes.c_longlong * (nc * 48))()
 lib.vlg_debug_tc_phase.argtypes = [ctypes.c_void_p, ctypes.c_int]
 assert lib.vlg_debug_tc_phase(ph, nc) == 0
 ph = np.array(ph).reshape(nc, 2, 24).astype(np.float64).mean(0)
-names = ["window setup", "F: sw wait + layer 1 + st", "F: wait F2", "F: E-F2", "F: wait F3", "F: E-F3", "bar after forward",
-         "energy pass", "B: G build + st", "B: wait B3", "B: E-B3", "B: wait B2", "B: E-B2", "bar after backward",
-         "domega + reductions", "step prologue/Adam", "F: item setup", "F: cp wait + group bar", "B: item setup", "B: cp wait + group bar",
-         "B: zs/bits loads", "-", "-", "-"]
+names = ["F: item setup + sw wait", "F: layer 1 + st + arrive", "F: wait F2", "F: E-F2", "F: wait F3", "F: E-F3",
+         "window setup + row lists", "bar after forward", "energy pass", "B: setup + G build + arrive", "B: wait B3", "B: E-B3",
+         "B: wait B2", "B: E-B2 (dz)", "bar after backward", "domega + reductions", "step prologue/Adam", "(skew F2)", "(skew F3)", "(skew B3)", "(skew B2)", "(last arrive -> issuer sees)", "(issuer: issue duration)", "(issued -> epilogue awake)"]
 for c in range(2):
-    tot = ph[c].sum()
+    tot = ph[c][:17].sum()
     print(f"chain {c}: total {tot:.0f} cycles")
     for i, nm in enumerate(names):
-        print(f"   {nm:28s} {ph[c, i]:10.0f}  {100 * ph[c, i] / tot:5.1f}%")
+        if nm != "-":
+            print(f"   {nm:28s} {ph[c, i]:10.0f}  {100 * ph[c, i] / tot:5.1f}%")
