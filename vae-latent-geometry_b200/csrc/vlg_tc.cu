@@ -55,19 +55,37 @@ namespace vlg {
 __device__ long long g_tc_stats[1024 * 8];
 #define STAT_T0() long long _t0 = clock64()
 #define STAT_ADD(var) var += clock64() - _t0
+// per-phase cycle accounting of the first warp of each epilogue group: [cta][chain][24]
+__device__ long long g_tc_phase[1024 * 48];
+#define PH_DECL() volatile long long ph_[24]; long long ph_t_ = clock64(); for (int i_ = 0; i_ < 24; ++i_) ph_[i_] = 0
+#define PH(i) do { if (tg == 0) { const long long n_ = clock64(); ph_[i] += n_ - ph_t_; ph_t_ = n_; } } while (0)
+// arrival skew inside a group: every epilogue warp notes when it arrived, the first warp of the group sees after the
+// round trip how much later the last one came
+#define ARR() do { if (lane == 0) arr_t_[ew] = clock64(); } while (0)
+#define SKEW(i) do { if (tg == 0) { long long mx_ = 0; for (int w_ = 0; w_ < 8; ++w_) mx_ = max(mx_, arr_t_[chain_id * 8 + w_]); \
+  ph_[i] += mx_ - arr_t_[ew]; ph_[21] += iss_t_[2 * chain_id] - mx_; ph_[22] += iss_t_[2 * chain_id + 1] - iss_t_[2 * chain_id]; ph_[23] += clock64() - iss_t_[2 * chain_id + 1]; } } while (0)
+#define PH_FLUSH() do { if (tg == 0 && blockIdx.x < 1024) for (int i_ = 0; i_ < 24; ++i_) g_tc_phase[(blockIdx.x * 2 + chain_id) * 24 + i_] = ph_[i_]; } while (0)
 #else
 #define STAT_T0()
 #define STAT_ADD(var)
+#define PH_DECL()
+#define PH(i)
+#define ARR()
+#define SKEW(i)
+#define PH_FLUSH()
 #endif
 
 namespace {
 
 using namespace tc;
 
-constexpr int TC_THREADS = 608;       // 3 control warps + 16 epilogue warps
+#ifndef VLG_TC_DUAL_ISSUE
+#define VLG_TC_DUAL_ISSUE 0           // 1: one MMA issuer warp per chain (see the issuer)
+#endif
+constexpr int TC_THREADS = VLG_TC_DUAL_ISSUE ? 640 : 608;   // 3 (4) control warps + 16 epilogue warps
 constexpr int GROUP_THREADS = 256;    // one epilogue group (chain)
 constexpr int EPI_THREADS = 512;
-constexpr int FIRST_EPI_WARP = 3;
+constexpr int FIRST_EPI_WARP = VLG_TC_DUAL_ISSUE ? 4 : 3;
 constexpr int STAGE_BYTES = 16384;
 constexpr int MAX_STAGES = 5;         // per chain
 constexpr int XD_STRIDE = 52;         // floats per stored decoder output row (X <= 52; 16 B rows)
@@ -120,13 +138,31 @@ __device__ __forceinline__ OpInfo op_info(int op) {
     default: return {OFF_W2T_UMMA, 4, 128, 4, 128, 0, 0};  // B2: D5(X) = A4(Y) * W2
   }
 }
-// hi / lo fp16 pairs of two fp32 values
+// hi / lo fp16 pairs of two fp32 values: hi = fp16(v), lo = fp16(v - hi).  The residual v - hi is exact in fp32 and
+// comes from one mixed-precision FMA per element (fma.rn.f32.f16: hi * -1 + v, SASS FHFMA) instead of a convert back
+// and a subtract -- 4 instructions per pair instead of 6, same bits.
+#ifndef VLG_OPT_FHFMA
+#define VLG_OPT_FHFMA 1
+#endif
 __device__ __forceinline__ void pack_hilo_h2(float a, float b, uint32_t& hi, uint32_t& lo) {
+#if !VLG_OPT_FHFMA
   const __half2 h = __floats2half2_rn(a, b);
   const float2 back = __half22float2(h);
   const __half2 l = __floats2half2_rn(a - back.x, b - back.y);
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&l);
+  return;
+#endif
+  float ra, rb;
+  asm("{\n\t.reg .b16 l, u, m1;\n\t"
+      "cvt.rn.f16x2.f32 %0, %4, %3;\n\t"
+      "mov.b32 {l, u}, %0;\n\t"
+      "mov.b16 m1, 0xBC00;\n\t"
+      "fma.rn.f32.f16 %1, l, m1, %3;\n\t"
+      "fma.rn.f32.f16 %2, u, m1, %4;\n\t}"
+      : "=&r"(hi), "=f"(ra), "=f"(rb)
+      : "f"(a), "f"(b));
+  asm("cvt.rn.f16x2.f32 %0, %2, %1;" : "=r"(lo) : "f"(ra), "f"(rb));
 }
 // two fp32 -> one fp16x2 word (round-to-nearest; lo half = first argument), optionally through relu
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
@@ -169,6 +205,10 @@ __device__ __forceinline__ uint32_t tf32_round_bits(uint32_t b) { return b + 0x1
 // intrinsics under nvcc 12.9 -- keep the float max.)
 __device__ __forceinline__ uint32_t relu_tf32(float v) { return __float_as_uint(fmaxf(v, 0.f)) + 0x1000u; }
 
+// 0xFF in byte j iff draw slot j of point pt holds decoder k (TcSmem::sel: one word per point)
+__device__ __forceinline__ uint32_t slot_match(const uint8_t* sel, int pt, int k) {
+  return __vcmpeq4(reinterpret_cast<const uint32_t*>(sel)[pt], uint32_t(k) * 0x01010101u);
+}
 __device__ __forceinline__ void named_bar(int id, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
@@ -228,7 +268,8 @@ __device__ __forceinline__ void acc_wait(uint64_t* bar, uint32_t parity, int lan
 struct TcSmem {
   unsigned char* ring;  // [chain][stage] 16 KB
   float* XD;            // [m][W][52] left-end outputs x1, then x2 - x1 (only when they fit: XL2 == 0; else in the workspace)
-  uint8_t* sel;         // [m][role][W] drawn decoder per segment (255: no segment)
+  uint8_t* sel;         // [W + 1][4] per POINT: the decoders drawn for the segments that meet there -- byte 2m: left end of its own
+                        // segment (MC sample m), byte 2m+1: right end of the previous one; 255: none.  One 32-bit load per row.
   uint16_t* rows;       // points of the window that drew decoder k, in increasing point order: rows[roff[k] .. + cnt[k])
   uint16_t* wcnt;       // [K][chunks of 512 points][16 warps] rows per (decoder, chunk, warp) (then: exclusive prefix)
   int* cnt;             // [K]
@@ -301,7 +342,7 @@ __device__ __forceinline__ TcSmem tc_carve(unsigned char* base, int W, int K, in
   s.XD = f; f += xd_in_smem ? M * W * XD_STRIDE : 0;
   s.zs = reinterpret_cast<float2*>(f); f += 2 * W;
   s.dzs = reinterpret_cast<float2*>(f); f += 2 * 4 * W;
-  s.sel = reinterpret_cast<uint8_t*>(f); f += TC_MAX_M * 2 * W / 4 + 1;
+  s.sel = reinterpret_cast<uint8_t*>(f); f += W + 1;
   s.wcnt = reinterpret_cast<uint16_t*>(f); f += K * tc_chunks(W) * 8;
   s.rows = reinterpret_cast<uint16_t*>(f);
   const size_t ring_off = (size_t(reinterpret_cast<unsigned char*>(f) - base) + size_t(2 * M) * W * 2 + 127) / 128 * 128;
@@ -314,7 +355,7 @@ __device__ __forceinline__ TcSmem tc_carve(unsigned char* base, int W, int K, in
 static size_t tc_smem_fixed_bytes(int W, int K, int M, int xl2) {
   // everything but the weight rings, in the order of tc_carve (+ alignment slack before the rings)
   const size_t fix = xl2 ? Fix<TC_MAX_G>::FLOATS : Fix<1>::FLOATS;
-  size_t fl = fix + (xl2 ? 0 : size_t(M) * W * XD_STRIDE) + 2 * size_t(W) + 2 * 4 * size_t(W) + TC_MAX_M * 2 * size_t(W) / 4 + 1 +
+  size_t fl = fix + (xl2 ? 0 : size_t(M) * W * XD_STRIDE) + 2 * size_t(W) + 2 * 4 * size_t(W) + size_t(W) + 1 +
               size_t(K) * tc_chunks(W) * 8;
   return (fl * 4 + size_t(2 * M) * W * 2 + 127) / 128 * 128;
 }
@@ -333,7 +374,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
   const int Wp = W / G;                   // points of one curve in a window
   constexpr bool F16 = FMT != FMT_TF32;   // fp16 operands (one or two terms)
   constexpr bool X3 = FMT == FMT_F16X3;   // 3-term split
+  constexpr bool DUAL_ISSUE = VLG_TC_DUAL_ISSUE != 0;   // one MMA issuer warp per chain
   extern __shared__ __align__(128) unsigned char smem_raw[];
+#ifdef VLG_TC_STATS
+  __shared__ volatile long long arr_t_[16];
+  __shared__ volatile long long iss_t_[4];   // [chain]{seen ready, issued}
+#endif
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int M = p.M, K = p.K, T = p.T, n_poly = p.n_poly, Kb = p.Kb;
   TcSmem s = tc_carve<GM>(smem_raw, W, K, M, !xl2);
@@ -379,7 +425,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *s.tmem_base;
-
   // Item i of a window (decoder k, rows 128q..128q+127 of k's row list) belongs to chain i & 1.
   // Per chain the tensor-core ops of a window are: for each of its items F2 F3, then (GRAD) for
   // each of its items B3 B2.  The item list of window w is published in ctl[w & 1] and
@@ -464,15 +509,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
         mbar_arrive(&ctl_free[w & 1]);   // done reading this window's item list
       }
     }
-  } else if (warp == 2) {
-    // ================= MMA issuer: serves whichever chain is ready =================
+  } else if (warp < FIRST_EPI_WARP) {
+    // ================= MMA issuer(s) =================
     // The whole warp runs this loop convergently; one elected lane's tcgen05 instructions take effect.
-    {
+    // DUAL_ISSUE = false: warp 2 serves whichever chain is ready (warp 3 idles); true: warp 2 + c serves chain c only.
+    // Two issuers interleave the chains' MMAs in the tensor pipe ("processor sharing": both GEMMs finish late) where
+    // one issuer runs them first come first served; measured: no gain in the 3-term mode, -2 % with single-term fp16
+    // operands (a fifth warp on one scheduler) -- off by default.
+    if (DUAL_ISSUE || warp == 2) {
+      const int c_lo = DUAL_ISSUE ? warp - 2 : 0, c_hi = DUAL_ISSUE ? warp - 1 : 2;
       const uint32_t leader = elect_one();
       int slot[2] = {0, 0}, opi[2] = {0, 0}, nitc[2] = {0, 0};
       int ops_left[2] = {0, 0};      // ops of the chain's current window still to issue
       long win[2] = {0, 0};          // next window whose item list the chain has to pick up
-      bool fin[2] = {false, false};
+      bool fin[2] = {c_lo > 0, c_hi < 2};
       uint32_t ph[2] = {0, 0}, ph_a[2] = {0, 0};
       long long w_full = 0, w_issue = 0;
       STAT_T0();
@@ -487,7 +537,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
         served = false;
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-          if (fin[c]) continue;
+          if (fin[c]) continue;   // (also: a chain another issuer serves)
           if (ops_left[c] == 0) {
             if (!mbar_test(win_ready, uint32_t(win[c] & 1))) continue;
             const int nit = s.ctl[win[c] & 1].nitems;
@@ -502,6 +552,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
           if (!mbar_test(&a_ready[c], ph_a[c])) continue;
           served = true;
           ph_a[c] ^= 1;
+#ifdef VLG_TC_STATS
+          if (lane == 0) iss_t_[2 * c] = clock64();
+#endif
           tc_fence_after();
           // op order inside a window: F2 F3 per item, then B3 B2 per item
           const int optype = (opi[c] < 2 * nitc[c]) ? (opi[c] & 1) : 2 + ((opi[c] - 2 * nitc[c]) & 1);
@@ -578,12 +631,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
             if (++slot[c] == nst) { slot[c] = 0; ph[c] ^= 1; }
           }
           umma_commit_elect(&acc_ready[c], leader);
+#ifdef VLG_TC_STATS
+          if (lane == 0) iss_t_[2 * c + 1] = clock64();
+#endif
           ++opi[c];
           --ops_left[c];
         }
       }
 #ifdef VLG_TC_STATS
-      if (lane == 0 && blockIdx.x < 1024) {
+      if (lane == 0 && blockIdx.x < 1024 && warp == 2) {
         g_tc_stats[blockIdx.x * 8 + 2] = w_full;
         g_tc_stats[blockIdx.x * 8 + 3] = clock64() - _t0;
         g_tc_stats[blockIdx.x * 8 + 5] = w_issue;
@@ -623,6 +679,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
     unsigned char* Gt = reinterpret_cast<unsigned char*>(X2 + size_t(M) * W * XD_STRIDE);
 
     for (int i = t512; i < 4 * n_poly * Kb; i += EPI_THREADS) s.basis[i] = p.basis[i];
+    PH_DECL();
     const int nchunk = XL2 ? tc_chunks(W) : 1;  // the window's points in chunks of 512 (thread = point)
 
     for (;;) {
@@ -684,6 +741,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
         if (t512 < G * 20) s.gacc[t512] = 0.f;
         if (t512 < G * 2) s.etot[t512] = 0.f;
         named_bar(3, EPI_THREADS);
+        PH(16);
 
         for (int win = 0; win < nwin; ++win, ++wcount) {
           const int seg0 = win * WSEG;
@@ -705,18 +763,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                     v = p.draws[(((size_t(n) * p.steps + step) * M + m) * 2 + role) * size_t(T - 1) + seg0 + i];
                     if (v >= K) { v = uint8_t(K - 1); bad_draw = true; }   // memory safety; reported through the status word
                   }
-                  s.sel[(m * 2 + role) * W + pt] = v;
+                  s.sel[4 * (pt + role) + 2 * m + role] = v;
                 }
+              if (M < 2) { s.sel[4 * pt + 2] = 255; s.sel[4 * pt + 7] = 255; }
             } else {
               uint32_t d[4] = {255u, 255u, 255u, 255u};
               if (seg_ok)
                 counter_draws4(p.seed, uint32_t(p.curve_id0 + n), uint32_t(p.step0 + step), uint32_t(seg0 + i), 0u,
                                uint32_t(K), d);
-              for (int q = 0; q < 4; ++q) {
-                const int m = q >> 1;
-                if (m < M) s.sel[(m * 2 + (q & 1)) * W + pt] = uint8_t(d[q]);
-              }
+              for (int q = 0; q < 4; ++q) s.sel[4 * (pt + (q & 1)) + q] = (q >> 1) < M ? uint8_t(d[q]) : uint8_t(255);
             }
+            if (pt == 0) { s.sel[1] = 255; s.sel[3] = 255; }   // no segment ends at the first point
           }
           for (int i = t512; i < 4 * W; i += EPI_THREADS) s.dzs[i] = make_float2(0.f, 0.f);
           named_bar(3, EPI_THREADS);
@@ -734,14 +791,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
 #pragma unroll
             for (int i = 0; i < 2 * TC_MAX_M; ++i) cand[i] = -1;
             if (pt < W) {
+              const uint32_t c4 = reinterpret_cast<const uint32_t*>(s.sel)[pt];
 #pragma unroll
-              for (int m = 0; m < TC_MAX_M; ++m)
-                if (m < M) {
-                  const int c0 = s.sel[(m * 2 + 0) * W + pt];                    // left end of its segment
-                  const int c1 = pt >= 1 ? int(s.sel[(m * 2 + 1) * W + pt - 1]) : 255;  // right end of the previous one
-                  if (c0 != 255) cand[2 * m] = c0;
-                  if (c1 != 255) cand[2 * m + 1] = c1;
-                }
+              for (int i = 0; i < 2 * TC_MAX_M; ++i) {
+                const int c = int((c4 >> (8 * i)) & 0xFFu);
+                if (c != 255) cand[i] = c;
+              }
 #pragma unroll
               for (int i = 1; i < 2 * TC_MAX_M; ++i)
 #pragma unroll
@@ -798,6 +853,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
           }
           named_bar(3, EPI_THREADS);
           const int nitems = ctl->nitems;
+          PH(6);
           // =============================== forward ===============================
           for (int it = chain_id; it < nitems; it += 2) {
             const int k = ctl->item[it] & 0xFF, q0 = (ctl->item[it] >> 8) * 128;
@@ -815,6 +871,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
             ++swj;
             const float2 z = s.zs[pt];
             const float2 zx2 = make_float2(z.x, z.x), zy2 = make_float2(z.y, z.y);
+            PH(0);
             // layer 1 (CUDA cores, fp32) -> A1 in X[col0 : col0+64]  (fp16: pairs in X[32 half : +32])
             if (F16) {
               if (wact) {
@@ -867,11 +924,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
             }
             tmem_wait_st();
             tc_fence_before();
-            mbar_arrive(&a_ready[chain_id]);
+            ARR(); mbar_arrive(&a_ready[chain_id]);
+            PH(1);
             // layer 2 epilogue: D2 (Y) -> relu(+b2) -> A2 (Y, in place), mask bits
             { STAT_T0(); acc_wait(&acc_ready[chain_id], ph_acc, lane); STAT_ADD(w_acc); }
             ph_acc ^= 1;
             tc_fence_after();
+            PH(2); SKEW(17);
             if (wact) {
               // two passes of 32 columns: one live 32-register tile instead of two (no spills)
               uint32_t bits[2];
@@ -922,11 +981,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
             }
             tmem_wait_st();
             tc_fence_before();
-            mbar_arrive(&a_ready[chain_id]);
+            ARR(); mbar_arrive(&a_ready[chain_id]);
+            PH(3);
             // layer 3 epilogue: D3 (X[0:64]) + b3 -> the slots of this point that drew decoder k
             { STAT_T0(); acc_wait(&acc_ready[chain_id], ph_acc, lane); STAT_ADD(w_acc); }
             ph_acc ^= 1;
             tc_fence_after();
+            PH(4); SKEW(18);
             if (wact) {
               uint32_t xv[32];
               tmem_ld32_sync((X3 ? colY : colX + (F16 ? 64 : 0)) + xc0, xv);
@@ -939,24 +1000,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                 x[j + 2] = __uint_as_float(xv[j + 2]) + bb.z;
                 x[j + 3] = __uint_as_float(xv[j + 3]) + bb.w;
               }
-              for (int m = 0; m < (active ? M : 0); ++m) {
-                // role 0: this point is the left end of its segment; role 1: right end of the previous one
-                if (s.sel[(m * 2 + 0) * W + pt] == k) {
-                  float4* d = reinterpret_cast<float4*>(X1 + (m * W + pt) * XD_STRIDE + xc0);
+              // the slots of this point that drew decoder k (one compare for all four).  Even slot 2m: this point is the left
+              // end of its segment (-> x1 row of the segment); odd slot 2m+1: right end of the previous one (-> x2 row)
+              const uint32_t eq = active ? slot_match(s.sel, pt, k) : 0u;
+#pragma unroll
+              for (int j = 0; j < 2 * TC_MAX_M; ++j)
+                if (eq & (1u << (8 * j))) {
+                  float4* d = reinterpret_cast<float4*>(((j & 1) ? X2 + ((j >> 1) * W + pt - 1) * XD_STRIDE
+                                                                 : X1 + ((j >> 1) * W + pt) * XD_STRIDE) + xc0);
 #pragma unroll
                   for (int q = 0; q < 8; ++q)
                     if (q < nq) d[q] = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
                 }
-                if (pt >= 1 && s.sel[(m * 2 + 1) * W + pt - 1] == k) {
-                  float4* d = reinterpret_cast<float4*>(X2 + (m * W + pt - 1) * XD_STRIDE + xc0);
-#pragma unroll
-                  for (int q = 0; q < 8; ++q)
-                    if (q < nq) d[q] = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
-                }
-              }
             }
+            PH(5);
           }
           named_bar(3, EPI_THREADS);
+          PH(7);
 
           // ============ x2 - x1, the energy, and the dE/dx operand tiles of the backward items ============
           if (GRAD) {
@@ -1015,10 +1075,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                 const bool wide = c < 6;   // chunk 6 = columns 48..51 (+ zero padding up to 55)
                 float4 dd[2 * TC_MAX_M][2];
                 bool on[2 * TC_MAX_M];
+                const uint32_t eq4 = slot_match(s.sel, pt, k);
 #pragma unroll
                 for (int m = 0; m < TC_MAX_M; ++m) {
-                  on[2 * m] = m < M && pt >= 1 && s.sel[(m * 2 + 1) * W + pt - 1] == k;   // right end of segment pt-1
-                  on[2 * m + 1] = m < M && s.sel[(m * 2 + 0) * W + pt] == k;              // left end of segment pt
+                  on[2 * m] = (eq4 >> (16 * m + 8)) & 1u;   // right end of segment pt-1
+                  on[2 * m + 1] = (eq4 >> (16 * m)) & 1u;   // left end of segment pt
                 }
 #pragma unroll
                 for (int j = 0; j < 2 * TC_MAX_M; ++j) {      // all loads first (L2 latency when xl2)
@@ -1111,6 +1172,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
             named_bar(3, EPI_THREADS);            // every tile of the window is written (and fenced for the async proxy)
             if (xl2 && t512 == 0) mbar_arrive(g_ready);  // -> the producers may bring them into shared memory
           }
+          PH(8);
 
           if (GRAD) {
             // =============================== backward ===============================
@@ -1139,15 +1201,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                 // only tells the issuer that the chain's accumulator columns are free (all tcgen05.ld of the
                 // previous item are complete in program order).
                 tc_fence_before();
-                mbar_arrive(&a_ready[chain_id]);
+                ARR(); mbar_arrive(&a_ready[chain_id]);
               } else {
                 // G = dE/dx_k (this point), columns xc0 .. xc0+31 -> X[xc0 : xc0+32]
                 if (wact) {
                   float g[32];
   #pragma unroll
                   for (int j = 0; j < 32; ++j) g[j] = 0.f;
-                  for (int m = 0; m < (active ? M : 0); ++m) {
-                    if (pt >= 1 && s.sel[(m * 2 + 1) * W + pt - 1] == k) {
+                  const uint32_t eq = active ? slot_match(s.sel, pt, k) : 0u;
+#pragma unroll
+                  for (int m = 0; m < TC_MAX_M; ++m) {     // same order of additions as ever: right end, then left end, per sample
+                    if (eq & (0x100u << (16 * m))) {
                       const float4* d = reinterpret_cast<const float4*>(X1 + (m * W + pt - 1) * XD_STRIDE + xc0);
   #pragma unroll
                       for (int q = 0; q < 8; ++q)
@@ -1156,7 +1220,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                           g[4 * q] += v.x; g[4 * q + 1] += v.y; g[4 * q + 2] += v.z; g[4 * q + 3] += v.w;
                         }
                     }
-                    if (s.sel[(m * 2 + 0) * W + pt] == k) {
+                    if (eq & (0x1u << (16 * m))) {
                       const float4* d = reinterpret_cast<const float4*>(X1 + (m * W + pt) * XD_STRIDE + xc0);
   #pragma unroll
                       for (int q = 0; q < 8; ++q)
@@ -1187,12 +1251,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                 }
                 tmem_wait_st();
                 tc_fence_before();
-                mbar_arrive(&a_ready[chain_id]);
+                ARR(); mbar_arrive(&a_ready[chain_id]);
               }
+              PH(9);
               // dh2 = (G W3) * mask2 -> A4 (Y, in place)
               { STAT_T0(); acc_wait(&acc_ready[chain_id], ph_acc, lane); STAT_ADD(w_acc); }
               ph_acc ^= 1;
               tc_fence_after();
+              PH(10); SKEW(19);
               if (half == 0 && pend_pt >= 0) {   // the previous item's row: both halves are in dzx now
                 const float2 u0 = s.dzx[(chain_id * 2 + 0) * 128 + row], u1 = s.dzx[(chain_id * 2 + 1) * 128 + row];
                 s.dzs[pend_slot * W + pend_pt] = make_float2(u0.x + u1.x, u0.y + u1.y);
@@ -1231,11 +1297,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
               }
               tmem_wait_st();
               tc_fence_before();
-              mbar_arrive(&a_ready[chain_id]);
+              ARR(); mbar_arrive(&a_ready[chain_id]);
+              PH(11);
               // dh1 = (dh2 W2) * mask1 (recomputed); dz[point] += dh1 W1 over this thread's 64 hidden units
               { STAT_T0(); acc_wait(&acc_ready[chain_id], ph_acc, lane); STAT_ADD(w_acc); }
               ph_acc ^= 1;
               tc_fence_after();
+              PH(12); SKEW(20);
               if (wact) {
                 float2 ax = make_float2(0.f, 0.f), ay = make_float2(0.f, 0.f);
 #pragma unroll
@@ -1262,10 +1330,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
               pend_pt = -1;
               if (active && half == 0) {
                 pend_pt = pt;
-                pend_slot = s.sel[pt] == k ? 0 : (pt >= 1 && s.sel[W + pt - 1] == k) ? 1 : (M > 1 && s.sel[2 * W + pt] == k) ? 2 : 3;
+                pend_slot = (__ffs(int(slot_match(s.sel, pt, k))) - 1) >> 3;   // first draw slot of the point that holds decoder k
               }
+              PH(13);
             }
             named_bar(3, EPI_THREADS);
+            PH(14);
             if (half == 0 && pend_pt >= 0) {     // the last item of each chain
               const float2 u0 = s.dzx[(chain_id * 2 + 0) * 128 + row], u1 = s.dzx[(chain_id * 2 + 1) * 128 + row];
               s.dzs[pend_slot * W + pend_pt] = make_float2(u0.x + u1.x, u0.y + u1.y);
@@ -1316,6 +1386,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
           } else {
             named_bar(3, EPI_THREADS);
           }
+          PH(15);
         }  // windows
 
         if (t512 < Gcur) {
@@ -1381,6 +1452,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
 #ifdef VLG_TC_STATS
     if (tg == 0 && blockIdx.x < 1024) g_tc_stats[blockIdx.x * 8 + 4 + chain_id * 2] = w_acc;
 #endif
+    PH_FLUSH();
     (void)w_acc;
   }
 
@@ -1470,6 +1542,9 @@ size_t tc_workspace_bytes(int N, int T, int K, int M) {
 #ifdef VLG_TC_STATS
 extern "C" int vlg_debug_tc_stats(long long* host_out, int n) {
   return cudaMemcpyFromSymbol(host_out, g_tc_stats, size_t(n) * 8 * sizeof(long long)) == cudaSuccess ? 0 : -3;
+}
+extern "C" int vlg_debug_tc_phase(long long* host_out, int n) {
+  return cudaMemcpyFromSymbol(host_out, g_tc_phase, size_t(n) * 48 * sizeof(long long)) == cudaSuccess ? 0 : -3;
 }
 #endif
 
