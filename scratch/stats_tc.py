@@ -33,9 +33,9 @@ assert lib.vlg_debug_tc_phase(ph, nc) == 0
 ph = np.array(ph).reshape(nc, 2, 24).astype(np.float64).mean(0)
 names = ["F: item setup + sw wait", "F: layer 1 + st + arrive", "F: wait F2", "F: E-F2", "F: wait F3", "F: E-F3",
          "window setup + row lists", "bar after forward", "energy pass", "B: setup + G build + arrive", "B: wait B3", "B: E-B3",
-         "B: wait B2", "B: E-B2 (dz)", "bar after backward", "domega + reductions", "step prologue/Adam", "(skew F2)", "(skew F3)", "(skew B3)", "(skew B2)", "(last arrive -> issuer sees)", "(issuer: issue duration)", "(issued -> epilogue awake)"]
+         "B: wait B2", "B: E-B2 (dz)", "bar after backward", "domega + reductions", "step prologue/Adam", "w: points/draws", "w: count pass", "w: scan + item list", "e: loads + diff loop", "e: warp sum", "d: first barrier", "d: design rows + warp sums + bar"]
 for c in range(2):
-    tot = ph[c][:17].sum()
+    tot = ph[c].sum()
     print(f"chain {c}: total {tot:.0f} cycles")
     for i, nm in enumerate(names):
         if nm != "-":

@@ -32,12 +32,19 @@
 // share a row (TMEM lane) and split its columns: four epilogue warps per scheduler hide TMEM /
 // shared-memory latency.
 //
-// Per window: draws -> per-decoder row lists (shared-memory atomics; row order does not affect
-// any result) -> forward items (layer 1 on CUDA cores, exact fp32) -> selected outputs stored
+// Per window: draws (one word per point: the decoders of the <= 4 segment ends that meet there) ->
+// per-decoder row lists in point order (warp ballots + scans: deterministic item membership) ->
+// forward items (layer 1 on CUDA cores, exact fp32) -> selected outputs stored
 // with plain stores, one writer per slot (left-end output x1 of a segment in shared memory,
 // right-end output x2 in an L2-resident workspace) -> one pass forms x2-x1 and the energy ->
 // backward items (input gradient only; layer-2 ReLU masks as bits in the workspace, layer-1
-// mask recomputed) -> dz per point -> d(omega).  Penalty gradient and Adam as in vlg_simt.cu.
+// mask recomputed) -> dz per (point, draw slot) cell -> d(omega).  Penalty gradient and Adam as in vlg_simt.cu.
+//
+// Where the time goes (VLG_TC_STATS build, per 128-row item of a chain, 3-term mode): 43 % epilogue phases
+// (7 per item, latency bound: two warps of a group per scheduler), 40 % waiting for the four GEMMs (a third of
+// it the MMAs themselves, the rest issue / commit / wake-up latency and the other chain's MMAs), 16 % per-window
+// phases (row lists, the x2-x1 pass: bandwidth of a 119 KB buffer, d(omega)).  Tensor memory holds two chains,
+// which is what bounds the overlap; see DESIGN.md 4.4 for the experiments that did not help.
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
@@ -63,7 +70,11 @@ __device__ long long g_tc_phase[1024 * 48];
 // round trip how much later the last one came
 #define ARR() do { if (lane == 0) arr_t_[ew] = clock64(); } while (0)
 #define SKEW(i) do { if (tg == 0) { long long mx_ = 0; for (int w_ = 0; w_ < 8; ++w_) mx_ = max(mx_, arr_t_[chain_id * 8 + w_]); \
-  ph_[i] += mx_ - arr_t_[ew]; ph_[21] += iss_t_[2 * chain_id] - mx_; ph_[22] += iss_t_[2 * chain_id + 1] - iss_t_[2 * chain_id]; ph_[23] += clock64() - iss_t_[2 * chain_id + 1]; } } while (0)
+  if (VLG_TC_STATS_SKEW) { ph_[i] += mx_ - arr_t_[ew]; ph_[21] += iss_t_[2 * chain_id] - mx_; ph_[22] += iss_t_[2 * chain_id + 1] - iss_t_[2 * chain_id]; ph_[23] += clock64() - iss_t_[2 * chain_id + 1]; } } } while (0)
+#ifndef VLG_TC_STATS_SKEW
+#define VLG_TC_STATS_SKEW 0   // 1: slots 17..23 = arrival skew / issuer timeline; 0: sub-phases of the per-window work
+#endif
+#define PHW(i) do { if (!VLG_TC_STATS_SKEW) PH(i); } while (0)
 #define PH_FLUSH() do { if (tg == 0 && blockIdx.x < 1024) for (int i_ = 0; i_ < 24; ++i_) g_tc_phase[(blockIdx.x * 2 + chain_id) * 24 + i_] = ph_[i_]; } while (0)
 #else
 #define STAT_T0()
@@ -72,6 +83,7 @@ __device__ long long g_tc_phase[1024 * 48];
 #define PH(i)
 #define ARR()
 #define SKEW(i)
+#define PHW(i)
 #define PH_FLUSH()
 #endif
 
@@ -208,6 +220,20 @@ __device__ __forceinline__ uint32_t relu_tf32(float v) { return __float_as_uint(
 // 0xFF in byte j iff draw slot j of point pt holds decoder k (TcSmem::sel: one word per point)
 __device__ __forceinline__ uint32_t slot_match(const uint8_t* sel, int pt, int k) {
   return __vcmpeq4(reinterpret_cast<const uint32_t*>(sel)[pt], uint32_t(k) * 0x01010101u);
+}
+// "operand ready" of an epilogue group: every thread has completed and fenced its tensor-memory stores; one arrival
+// per warp (the mbarrier counts the group's 8 warps) instead of 256 serialized arrivals on one shared-memory word
+#ifndef VLG_TC_WARP_ARRIVE
+#define VLG_TC_WARP_ARRIVE 1
+#endif
+__device__ __forceinline__ void group_arrive(uint64_t* bar, int lane) {
+#if VLG_TC_WARP_ARRIVE
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar);
+#else
+  (void)lane;
+  mbar_arrive(bar);
+#endif
 }
 __device__ __forceinline__ void named_bar(int id, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
@@ -407,8 +433,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
     }
-    mbar_init(&a_ready[0], GROUP_THREADS);
-    mbar_init(&a_ready[1], GROUP_THREADS);
+    mbar_init(&a_ready[0], VLG_TC_WARP_ARRIVE ? GROUP_THREADS / 32 : GROUP_THREADS);
+    mbar_init(&a_ready[1], VLG_TC_WARP_ARRIVE ? GROUP_THREADS / 32 : GROUP_THREADS);
     mbar_init(&acc_ready[0], 1);
     mbar_init(&acc_ready[1], 1);
     mbar_init(win_ready, 1);
@@ -777,6 +803,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
           }
           for (int i = t512; i < 4 * W; i += EPI_THREADS) s.dzs[i] = make_float2(0.f, 0.f);
           named_bar(3, EPI_THREADS);
+          PHW(17);
           // ---- per-decoder row lists, in increasing point order ----
           // Item membership must not depend on thread timing: a decoder drawn by more than 128 points of
           // the window is split into several items, which run on different chains, and the chains' dz
@@ -814,33 +841,51 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
             }
           }
           named_bar(3, EPI_THREADS);
-          if (t512 < K) {
-            int acc = 0;
-            for (int w = 0; w < nchunk * 16; ++w) {
-              const int c = s.wcnt[t512 * nchunk * 16 + w];
-              s.wcnt[t512 * nchunk * 16 + w] = uint16_t(acc);
-              acc += c;
+          PHW(18);
+          if (t512 < 32) {
+            // One warp, lane = decoder (32 at a time): the scan over (chunk, warp) per decoder, then warp scans over the
+            // decoders for the list offsets and the item numbers; every lane writes its decoder's items.
+            // The control warps must be done with the item list this one replaces (window wcount - 2).
+            if (lane == 0 && wcount >= 2) mbar_wait(&ctl_free[wcount & 1], uint32_t(((wcount >> 1) - 1) & 1));
+            __syncwarp();
+            int off_carry = 0, ni_carry = 0;
+            for (int k0 = 0; k0 < K; k0 += 32) {
+              const int k = k0 + lane;
+              int acc = 0;
+              if (k < K)
+                for (int w = 0; w < nchunk * 16; ++w) {
+                  const int c = s.wcnt[k * nchunk * 16 + w];
+                  s.wcnt[k * nchunk * 16 + w] = uint16_t(acc);
+                  acc += c;
+                }
+              const int nit = (acc + 127) >> 7;
+              int so = acc, si = nit;   // inclusive scans over the lanes
+#pragma unroll
+              for (int o = 1; o < 32; o <<= 1) {
+                const int a = __shfl_up_sync(0xffffffffu, so, o), b = __shfl_up_sync(0xffffffffu, si, o);
+                if (lane >= o) { so += a; si += b; }
+              }
+              if (k < K) {
+                s.cnt[k] = acc;
+                s.roff[k] = off_carry + so - acc;
+                const int i0 = ni_carry + si - nit;
+                for (int q = 0; q < nit; ++q) ctl->item[i0 + q] = uint16_t(k | (q << 8));
+              }
+              off_carry += __shfl_sync(0xffffffffu, so, 31);
+              ni_carry += __shfl_sync(0xffffffffu, si, 31);
             }
-            s.cnt[t512] = acc;
-          }
-          named_bar(3, EPI_THREADS);
-          if (t512 == 0) {
-            // the control warps must be done with the item list this one replaces (window wcount - 2)
-            if (wcount >= 2) mbar_wait(&ctl_free[wcount & 1], uint32_t(((wcount >> 1) - 1) & 1));
-            int ni = 0, off = 0;
-            for (int k = 0; k < K; ++k) {
-              s.roff[k] = off;
-              off += s.cnt[k];
-              for (int q = 0; q * 128 < s.cnt[k]; ++q) ctl->item[ni++] = uint16_t(k | (q << 8));
+            if (lane == 0) {
+              ctl->nitems = ni_carry;
+              ctl->base = dec_base;
+              n_items += unsigned(ni_carry);
+              n_rows += unsigned(off_carry);
             }
-            ctl->nitems = ni;
-            ctl->base = dec_base;
-            n_items += unsigned(ni);
-            n_rows += unsigned(off);
             __threadfence_block();
-            mbar_arrive(win_ready);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(win_ready);
           }
           named_bar(3, EPI_THREADS);
+          PHW(19);
           for (int ch = 0; ch < nchunk; ++ch) {
             int cand[2 * TC_MAX_M];
             const int pt = ch * 512 + t512;
@@ -924,7 +969,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
             }
             tmem_wait_st();
             tc_fence_before();
-            ARR(); mbar_arrive(&a_ready[chain_id]);
+            ARR(); group_arrive(&a_ready[chain_id], lane);
             PH(1);
             // layer 2 epilogue: D2 (Y) -> relu(+b2) -> A2 (Y, in place), mask bits
             { STAT_T0(); acc_wait(&acc_ready[chain_id], ph_acc, lane); STAT_ADD(w_acc); }
@@ -981,7 +1026,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
             }
             tmem_wait_st();
             tc_fence_before();
-            ARR(); mbar_arrive(&a_ready[chain_id]);
+            ARR(); group_arrive(&a_ready[chain_id], lane);
             PH(3);
             // layer 3 epilogue: D3 (X[0:64]) + b3 -> the slots of this point that drew decoder k
             { STAT_T0(); acc_wait(&acc_ready[chain_id], ph_acc, lane); STAT_ADD(w_acc); }
@@ -1025,6 +1070,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
             // place of x1), four independent pieces per thread in flight.  The energy is the plain sum of squares,
             // in a fixed order (deterministic).
             const int n4 = nseg * (XD_STRIDE / 4);
+            if (!xl2) {
+              // one curve, x1 in shared memory: both MC samples in one index space, eight x2 pieces (L2) in flight per thread
+              constexpr int NV = XD_STRIDE / 4, NB = 8;
+              const int ntot = M * n4;
+              const float4* x2 = reinterpret_cast<const float4*>(X2);
+              float4* x1 = reinterpret_cast<float4*>(X1);
+              float e = 0.f;
+              for (int i0 = t512; i0 < ntot; i0 += NB * EPI_THREADS) {
+                float4 v[NB];
+                int ad[NB];
+#pragma unroll
+                for (int j = 0; j < NB; ++j) {
+                  const int idx = i0 + j * EPI_THREADS;
+                  const int m = idx / n4;
+                  ad[j] = idx < ntot ? m * W * NV + (idx - m * n4) : -1;
+                  v[j] = ad[j] >= 0 ? __ldcg(x2 + ad[j]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int j = 0; j < NB; ++j)
+                  if (ad[j] >= 0) {
+                    const float4 u = x1[ad[j]];
+                    const float4 a = make_float4(v[j].x - u.x, v[j].y - u.y, v[j].z - u.z, v[j].w - u.w);
+                    x1[ad[j]] = a;
+                    e = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(a.z, a.z, fmaf(a.w, a.w, e))));
+                  }
+              }
+              PHW(20);
+              e = warp_sum(e);
+              if (lane == 0) s.red[320 + ew] = e;
+              PHW(21);
+            } else
             for (int jc = 0; jc < Gcur; ++jc) {      // the segments of one curve are contiguous rows: its energy
               float e = 0.f;
               for (int m = 0; m < M; ++m) {
@@ -1201,7 +1277,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                 // only tells the issuer that the chain's accumulator columns are free (all tcgen05.ld of the
                 // previous item are complete in program order).
                 tc_fence_before();
-                ARR(); mbar_arrive(&a_ready[chain_id]);
+                ARR(); group_arrive(&a_ready[chain_id], lane);
               } else {
                 // G = dE/dx_k (this point), columns xc0 .. xc0+31 -> X[xc0 : xc0+32]
                 if (wact) {
@@ -1251,7 +1327,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                 }
                 tmem_wait_st();
                 tc_fence_before();
-                ARR(); mbar_arrive(&a_ready[chain_id]);
+                ARR(); group_arrive(&a_ready[chain_id], lane);
               }
               PH(9);
               // dh2 = (G W3) * mask2 -> A4 (Y, in place)
@@ -1297,7 +1373,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
               }
               tmem_wait_st();
               tc_fence_before();
-              ARR(); mbar_arrive(&a_ready[chain_id]);
+              ARR(); group_arrive(&a_ready[chain_id], lane);
               PH(11);
               // dh1 = (dh2 W2) * mask1 (recomputed); dz[point] += dh1 W1 over this thread's 64 hidden units
               { STAT_T0(); acc_wait(&acc_ready[chain_id], ph_acc, lane); STAT_ADD(w_acc); }
@@ -1342,6 +1418,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
             }
           }
           named_bar(3, EPI_THREADS);
+          PHW(22);
           // ---- energy of the window per curve; d(omega) += P^T dz over the points of the window ----
           if (t512 < Gcur) {
             float ee = 0.f, ll = 0.f;
@@ -1375,6 +1452,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                   if (lane == 0) { s.red[wpos * 20 + 2 * k] = cx; s.red[wpos * 20 + 2 * k + 1] = cy; }
                 }
               named_bar(3, EPI_THREADS);
+              PHW(23);
               if (t512 < 2 * Kb) {
                 for (int w = 0; w < 16; ++w) {
                   const int p0 = ch * 512 + w * 32;
