@@ -243,10 +243,10 @@ def test_errors_are_loud(vlg):
     dec = make_decoders(vlg, g, 4)
     t = torch.linspace(0, 1, 130, device="cuda")
     with pytest.raises(vlg.VlgError):
-        vlg.optimize_splines(model, dec, t, 1, M=9, precision="fp32")        # M too large
-    with pytest.warns(UserWarning):                                          # M = 3: tf32 request served by the fp32 kernel
-        e3 = vlg.optimize_splines(make_model(vlg, g), dec, t, 1, M=3, seed=1, precision="tf32")
-    assert torch.equal(e3, vlg.optimize_splines(make_model(vlg, g), dec, t, 1, M=3, seed=1, precision="fp32"))
+        vlg.optimize_splines(model, dec, t, 1, M=9, precision="fp32")        # M too large for the fp32 kernel
+    with pytest.warns(UserWarning):                                          # one decoder: tf32 request served by the fp32 kernel
+        e3 = vlg.optimize_splines(make_model(vlg, g), dec[:1], t, 1, M=3, seed=1, precision="tf32")
+    assert torch.equal(e3, vlg.optimize_splines(make_model(vlg, g), dec[:1], t, 1, M=3, seed=1, precision="fp32"))
     with pytest.raises(vlg.VlgError):
         vlg.optimize_splines(model, dec, t.cpu(), 1, M=1, precision="fp32")  # CPU tensor
     with pytest.raises(vlg.VlgError):
@@ -395,12 +395,15 @@ def test_final_length_after_150_steps(vlg, prec, tol):
 
 
 @pytest.mark.parametrize("T,N,K,M,n_poly", [(2, 1, 1, 1, 1), (3, 2, 2, 2, 2), (128, 3, 3, 2, 4), (255, 2, 5, 1, 8),
-                                           (256, 1, 16, 2, 4), (257, 2, 4, 2, 4), (600, 3, 1, 1, 4), (513, 150, 7, 2, 4)])
+                                           (256, 1, 16, 2, 4), (257, 2, 4, 2, 4), (600, 3, 1, 1, 4), (513, 150, 7, 2, 4),
+                                           (300, 3, 6, 3, 4), (700, 2, 10, 4, 4), (130, 2, 3, 4, 2)])
 @pytest.mark.parametrize("tc", TC_PRECISIONS)
 def test_tf32_edge_shapes_against_fp32_kernel(vlg, T, N, K, M, n_poly, tc):
     """Window boundaries (255/256/257 points), a decoder drawn by more than 128 points of a window
     (K=1: two 128-row items per window), a single segment, more curves than SMs (persistent CTAs
-    walk several curves), K up to 16.  Compared against the fp32 kernel on identical draws."""
+    walk several curves), K up to 16, more than two MC samples (the tensor-core kernel works through them in blocks
+    of two; the reference exposes --mc-samples freely, src/optimize.py:232).  Compared against the fp32 kernel on
+    identical draws."""
     rng = np.random.default_rng(T * 131 + K)
     W = dict(W1=rng.normal(size=(K, 128, 2)) * 0.7, b1=rng.normal(size=(K, 128)) * 0.3,
              W2=rng.normal(size=(K, 128, 128)) * 0.09, b2=rng.normal(size=(K, 128)) * 0.1,
@@ -433,6 +436,47 @@ def test_tf32_edge_shapes_against_fp32_kernel(vlg, T, N, K, M, n_poly, tc):
     # Adam's first steps move every coefficient by ~lr whatever the gradient size, so a sign flip of a
     # near-zero gradient component costs up to 2*lr per step; frequent for K = 1 (noisy TF32 gradient)
     assert np.abs(res[tc][1] - res["fp32"][1]).max() < (2.0 if K == 1 else 0.25) * S * 1e-3 + 1e-6
+
+
+@pytest.mark.parametrize("M", [3, 4])
+def test_more_than_two_mc_samples_fp32_grade(vlg, M):
+    """M > 2 on the tensor-core kernel (blocks of two samples), 3-term mode: fp32-grade agreement with the fp32
+    kernel on the real ensemble, energies AND the omega after a few Adam steps; same draw stream (Philox keyed on the
+    sample pair)."""
+    g = Hh.load("ens_seed12_euclid")
+    K, T = int(g["K"]), 500
+    dec = make_decoders(vlg, g, K)
+    t = torch.linspace(0, 1, T, device="cuda")
+    res = {}
+    for prec in ("fp32", "f16x3"):
+        model = make_model(vlg, g)
+        _, trace = vlg.optimize_splines(model, dec, t, 4, M=M, seed=3, precision=prec, return_trace=True)
+        res[prec] = (trace.cpu().numpy(), model.omega.cpu().numpy())
+    rel = np.abs(res["f16x3"][0] / res["fp32"][0] - 1).max()
+    print(f"\nM={M}: f16x3 vs fp32 kernel, per-step energy max rel {rel:.2e}")
+    assert rel < 2e-5
+    assert np.abs(res["f16x3"][1] - res["fp32"][1]).max() < 2e-4
+
+
+def test_six_mc_samples_against_the_oracle(vlg):
+    """M = 6 (three sample blocks; beyond what the fp32 kernel holds) with explicit draws, 3-term mode, against the
+    fp64 oracle: per-step energies of 3 Adam steps."""
+    from oracle import geodesic_oracle as O
+    g = Hh.load("synth_np4_T130")
+    K, T, M, S = int(g["K"]), int(g["T"]), 6, 3
+    N = g["a"].shape[0]
+    draws = np.random.default_rng(5).integers(0, K, size=(S, M, 2, T - 1, N))
+    arrs = Hh.decoder_arrays(g)
+    ref = O.optimize_steps(g["a"].astype(np.float64), g["b"].astype(np.float64), g["omega_init"].astype(np.float64),
+                           g["basis"].astype(np.float64), Hh.tgrid(T, np.float64), int(g["n_poly"]),
+                           Hh.decoder_list(arrs, K, np.float64), draws, S)
+    model = make_model(vlg, g)
+    _, trace = vlg.optimize_splines(model, make_decoders(vlg, g, K), torch.linspace(0, 1, T, device="cuda"), S, M=M,
+                                    draws=draws, precision="f16x3", return_trace=True)
+    rel = np.abs(trace.cpu().numpy() / ref["energy"] - 1).max()
+    print(f"\nM=6, f16x3 vs fp64 oracle: per-step energy max rel {rel:.2e}")
+    assert rel < 2e-5
+    assert np.abs(model.omega.cpu().numpy() - ref["omega"]).max() < 2e-5
 
 
 @pytest.mark.parametrize("tc", TC_PRECISIONS)

@@ -107,7 +107,7 @@ constexpr int TC_MAX_W = 512;         // points per window, one curve per window
 constexpr int TC_MAX_WG = 2048;       // points per window when it holds several whole curves (XL2 kernels)
 constexpr int TC_MAX_G = 8;           // curves per window (XL2 kernels)
 constexpr int OM_STRIDE = 6 * MAX_KB + 2;   // per-curve omega | adam m | adam v
-constexpr int TC_MAX_M = 2;           // MC samples supported by this kernel
+constexpr int TC_MAX_M = 2;           // MC samples per block (any number of samples: blocks of two)
 constexpr int TC_MAX_K = 64;          // decoders
 constexpr int MAX_ITEMS = TC_MAX_K + 2 * TC_MAX_M * TC_MAX_WG / 128 + 8;  // sum_k ceil(n_k/128) <= K + 2*M*W/128
 
@@ -407,7 +407,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
   __shared__ volatile long long iss_t_[4];   // [chain]{seen ready, issued}
 #endif
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int M = p.M, K = p.K, T = p.T, n_poly = p.n_poly, Kb = p.Kb;
+  // MC samples are processed two at a time ("sample blocks": one Philox call = the four draws of two samples, four draw
+  // slots per point); M below is the capacity of a block, Mtot the number of samples the energy averages over
+  const int Mtot = p.M, M = min(p.M, TC_MAX_M), K = p.K, T = p.T, n_poly = p.n_poly, Kb = p.Kb;
   TcSmem s = tc_carve<GM>(smem_raw, W, K, M, !xl2);
   const int WSEG = Wp - 1;  // segments of one curve per window
   uint64_t* full = s.bars;                       // [2][MAX_STAGES]
@@ -691,7 +693,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
     float* swbuf = s.sw + chain_id * SW_SLOTS * 576;
     unsigned swj = 0;                           // stream index of this chain's items, as in the producer
     uint32_t ph_acc = 0;
-    const float coefm = 2.0f / float(M);
+    const float coefm = 2.0f / float(Mtot);
     long long w_acc = 0;
     long wcount = 0;                            // windows processed by this CTA so far
     bool bad_draw = false;                      // an explicit draw was >= K (clamped)
@@ -769,7 +771,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
         named_bar(3, EPI_THREADS);
         PH(16);
 
-        for (int win = 0; win < nwin; ++win, ++wcount) {
+        // one pass of the window body per (window, sample block): to the control warps a block is just another window
+        for (int win = 0; win < nwin; ++win)
+        for (int mb = 0; 2 * mb < Mtot; ++mb, ++wcount) {
+          const int Mb = min(TC_MAX_M, Mtot - 2 * mb);   // samples of this block
           const int seg0 = win * WSEG;
           const int nseg = min(WSEG, T - 1 - seg0);   // segments of every curve in this window
           WinCtl* ctl = &s.ctl[wcount & 1];
@@ -782,22 +787,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
             const bool seg_ok = i < nseg && j < Gcur;
             const int n = n0 + j;
             if (p.draws != nullptr) {
-              for (int m = 0; m < M; ++m)
+              for (int m = 0; m < Mb; ++m)
                 for (int role = 0; role < 2; ++role) {
                   uint8_t v = 255;
                   if (seg_ok) {
-                    v = p.draws[(((size_t(n) * p.steps + step) * M + m) * 2 + role) * size_t(T - 1) + seg0 + i];
+                    v = p.draws[(((size_t(n) * p.steps + step) * Mtot + 2 * mb + m) * 2 + role) * size_t(T - 1) + seg0 + i];
                     if (v >= K) { v = uint8_t(K - 1); bad_draw = true; }   // memory safety; reported through the status word
                   }
                   s.sel[4 * (pt + role) + 2 * m + role] = v;
                 }
-              if (M < 2) { s.sel[4 * pt + 2] = 255; s.sel[4 * pt + 7] = 255; }
+              if (Mb < 2) { s.sel[4 * pt + 2] = 255; s.sel[4 * pt + 7] = 255; }
             } else {
               uint32_t d[4] = {255u, 255u, 255u, 255u};
               if (seg_ok)
-                counter_draws4(p.seed, uint32_t(p.curve_id0 + n), uint32_t(p.step0 + step), uint32_t(seg0 + i), 0u,
+                counter_draws4(p.seed, uint32_t(p.curve_id0 + n), uint32_t(p.step0 + step), uint32_t(seg0 + i), uint32_t(mb),
                                uint32_t(K), d);
-              for (int q = 0; q < 4; ++q) s.sel[4 * (pt + (q & 1)) + q] = (q >> 1) < M ? uint8_t(d[q]) : uint8_t(255);
+              for (int q = 0; q < 4; ++q) s.sel[4 * (pt + (q & 1)) + q] = (q >> 1) < Mb ? uint8_t(d[q]) : uint8_t(255);
             }
             if (pt == 0) { s.sel[1] = 255; s.sel[3] = 255; }   // no segment ends at the first point
           }
@@ -1073,7 +1078,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
             if (!xl2) {
               // one curve, x1 in shared memory: both MC samples in one index space, eight x2 pieces (L2) in flight per thread
               constexpr int NV = XD_STRIDE / 4, NB = 8;
-              const int ntot = M * n4;
+              const int ntot = Mb * n4;
               const float4* x2 = reinterpret_cast<const float4*>(X2);
               float4* x1 = reinterpret_cast<float4*>(X1);
               float e = 0.f;
@@ -1103,7 +1108,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
             } else
             for (int jc = 0; jc < Gcur; ++jc) {      // the segments of one curve are contiguous rows: its energy
               float e = 0.f;
-              for (int m = 0; m < M; ++m) {
+              for (int m = 0; m < Mb; ++m) {
                 const float4* x2 = reinterpret_cast<const float4*>(X2 + size_t(m * W + jc * Wp) * XD_STRIDE);
                 float4* x1 = reinterpret_cast<float4*>(X1 + size_t(m * W + jc * Wp) * XD_STRIDE);
                 for (int i0 = t512; i0 < n4; i0 += 4 * EPI_THREADS) {
@@ -1210,7 +1215,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
             const int sub = lane & 15;
             constexpr int NV = XD_STRIDE / 4;   // 13 float4 per row
             constexpr int UNR = 6;
-            const int nent = M * Wp;            // (m, local point) entries of one curve
+            const int nent = Mb * Wp;           // (m, local point) entries of one curve
             for (int jc = 0; jc < Gcur; ++jc) {
               float e = 0.f, l = 0.f;
               for (int base = ew * 2 + (lane >> 4); base < nent; base += 32 * UNR) {
@@ -1387,15 +1392,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                   uint32_t v[32];
                   tmem_ld32_sync((F16 ? colY : colX) + col0 + 32 * hh, v);
 #pragma unroll
-                  for (int j = 0; j < 32; j += 2) {
+                  for (int j = 0; j < 32; j += 4) {   // 16-byte loads of the (warp-uniform) layer-1 weights
                     const int c = col0 + 32 * hh + j;
-                    const float2 wx = *reinterpret_cast<const float2*>(sw + OFF_W1X + c);
-                    const float2 wy = *reinterpret_cast<const float2*>(sw + OFF_W1Y + c);
-                    const float2 bb = *reinterpret_cast<const float2*>(sw + OFF_B1 + c);
-                    const float2 h = __ffma2_rn(wy, zy2, __ffma2_rn(wx, zx2, bb));
-                    const float2 dh = make_float2(h.x > 0.f ? __uint_as_float(v[j]) : 0.f, h.y > 0.f ? __uint_as_float(v[j + 1]) : 0.f);
-                    ax = __ffma2_rn(dh, wx, ax);
-                    ay = __ffma2_rn(dh, wy, ay);
+                    const float4 wx4 = *reinterpret_cast<const float4*>(sw + OFF_W1X + c);
+                    const float4 wy4 = *reinterpret_cast<const float4*>(sw + OFF_W1Y + c);
+                    const float4 bb4 = *reinterpret_cast<const float4*>(sw + OFF_B1 + c);
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {     // same pair order as ever: (c, c+1), then (c+2, c+3)
+                      const float2 wx = e ? make_float2(wx4.z, wx4.w) : make_float2(wx4.x, wx4.y);
+                      const float2 wy = e ? make_float2(wy4.z, wy4.w) : make_float2(wy4.x, wy4.y);
+                      const float2 bb = e ? make_float2(bb4.z, bb4.w) : make_float2(bb4.x, bb4.y);
+                      const float2 h = __ffma2_rn(wy, zy2, __ffma2_rn(wx, zx2, bb));
+                      const float2 dh = make_float2(h.x > 0.f ? __uint_as_float(v[j + 2 * e]) : 0.f,
+                                                    h.y > 0.f ? __uint_as_float(v[j + 2 * e + 1]) : 0.f);
+                      ax = __ffma2_rn(dh, wx, ax);
+                      ay = __ffma2_rn(dh, wy, ay);
+                    }
                   }
                 }
                 if (active) {
@@ -1469,13 +1481,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
 
         if (t512 < Gcur) {
           const int n = n0 + t512;
-          const float E = s.etot[2 * t512] / float(M);
+          const float E = s.etot[2 * t512] / float(Mtot);
           // fp16 operands overflow above 65504: inf/NaN reach the energy (forward) or omega (backward)
           if (!(fabsf(E) <= 3.0e38f)) atomicOr(&queue[1], unsigned(VLG_STATUS_NONFINITE));
           if (p.energy_trace) p.energy_trace[size_t(step) * p.N + n] = E;
           if (step == p.steps - 1) {
             if (p.energy_last) p.energy_last[n] = E;
-            if (p.length_out) p.length_out[n] = s.etot[2 * t512 + 1] / float(M);
+            if (p.length_out) p.length_out[n] = s.etot[2 * t512 + 1] / float(Mtot);
           }
         }
         if (GRAD && t512 < Gcur * 2 * Kb) {
@@ -1566,6 +1578,7 @@ static double tc_expected_items(int w, double p) {
   return items;
 }
 static TcPlan tc_plan(int T, int K, int M, bool allow_multi) {
+  if (M > TC_MAX_M) M = TC_MAX_M;   // samples per block
   const double p = 1.0 - pow(1.0 - 1.0 / K, 2.0 * M);
   const int segs = T - 1;
   int force_nwin = 0, force_xl2 = -1, force_g = 0;
@@ -1610,7 +1623,8 @@ static TcPlan tc_plan(int T, int K, int M, bool allow_multi) {
 }
 
 size_t tc_workspace_bytes(int N, int T, int K, int M) {
-  if (M > TC_MAX_M || K > TC_MAX_K) return 0;
+  if (K > TC_MAX_K) return 0;
+  if (M > TC_MAX_M) M = TC_MAX_M;   // buffers are sized for one block of samples
   const TcPlan pl = tc_plan(T, K, M, true);   // the multi-curve plan needs at least as much as the single-curve one
   const TcPlan p1 = tc_plan(T, K, M, false);
   const size_t a = tc_ws_cta_words(K, M, pl.W), b = tc_ws_cta_words(K, M, p1.W);
@@ -1629,12 +1643,13 @@ extern "C" int vlg_debug_tc_phase(long long* host_out, int n) {
 cudaError_t launch_tc(const StepParams& p, bool grad, cudaStream_t stream) {
   if (p.precision < 1 || p.precision > 3) return cudaErrorNotSupported;
   const int fmt = p.precision == 1 ? FMT_TF32 : p.precision == 3 ? FMT_F16 : FMT_F16X3;
-  if (p.M > TC_MAX_M || p.K > TC_MAX_K) return cudaErrorNotSupported;
-  const TcPlan pl = tc_plan(p.T, p.K, p.M, p.dec_base == nullptr);   // per-curve weight sets: one curve per window
+  if (p.K > TC_MAX_K || p.M < 1) return cudaErrorNotSupported;
+  const int Mc = p.M > TC_MAX_M ? TC_MAX_M : p.M;
+  const TcPlan pl = tc_plan(p.T, p.K, Mc, p.dec_base == nullptr);   // per-curve weight sets: one curve per window
   const int W = pl.W, nst = pl.nst, xl2 = pl.xl2, G = pl.G;
   if (W < 2 || nst < 2) return cudaErrorNotSupported;
   if (p.workspace == nullptr || p.workspace_bytes < tc_workspace_bytes(p.N, p.T, p.K, p.M)) return cudaErrorInvalidValue;
-  const size_t smem = tc_smem_fixed_bytes(W, p.K, p.M, xl2) + size_t(2) * nst * STAGE_BYTES;
+  const size_t smem = tc_smem_fixed_bytes(W, p.K, Mc, xl2) + size_t(2) * nst * STAGE_BYTES;
   const int ngroups = (p.N + G - 1) / G;
   const int grid = tc_grid(ngroups);
   StepParams q = p;
