@@ -159,7 +159,8 @@ def test_cov_shrinks_with_more_decoders_on_the_committed_checkpoints(built_lib):
     assert cov[10] < cov[1]
 
 
-def test_single_decoder_dropin_reproduces_committed_lengths(tmp_path, built_lib):
+@pytest.mark.parametrize("prec", ["fp32", "f16x3"])
+def test_single_decoder_dropin_reproduces_committed_lengths(tmp_path, built_lib, prec):
     """BASELINE config 2 through the drop-in CLI module: 64 curves of the reference's committed input
     (src/artifacts/spline_batch_seed123.pt), 500 steps, against the length_geodesic the reference committed in
     spline_batch_optimized_batched_seed123.pt: <= 3e-3 relative (the reference's own re-run on
@@ -184,7 +185,7 @@ def test_single_decoder_dropin_reproduces_committed_lengths(tmp_path, built_lib)
     sys.path.insert(0, str(ROOT))
     import importlib
     mod = importlib.import_module("src.single_decoder.optimize_energy_batched")
-    out_path = mod.main(123, "src/artifacts/selected_pairs_64.json", steps=int(g["steps"]), artifact_dir=str(art))
+    out_path = mod.main(123, "src/artifacts/selected_pairs_64.json", steps=int(g["steps"]), precision=prec, artifact_dir=str(art))
     recs = torch.load(out_path, map_location="cpu", weights_only=False)
     assert isinstance(recs, list) and len(recs) == 64
     assert list(recs[0].keys()) == ["a", "b", "cluster_pair", "n_poly", "basis", "omega_init", "omega_optimized",
@@ -193,7 +194,7 @@ def test_single_decoder_dropin_reproduces_committed_lengths(tmp_path, built_lib)
     ref = g["committed_length_geodesic"]
     err = np.abs(got / ref - 1)
     spread = np.abs(g["rerun_length_f32"] / ref - 1)
-    print(f"\nsingle decoder, 64 curves x 500 steps: length vs committed: median {np.median(err):.2e}, max {err.max():.2e}; "
+    print(f"\nsingle decoder [{prec}], 64 curves x 500 steps: length vs committed: median {np.median(err):.2e}, max {err.max():.2e}; "
           f"reference CPU re-run vs committed: median {np.median(spread):.2e}, max {spread.max():.2e}")
     # 500 Adam steps amplify rounding-level differences on a few curves: the reference's own CPU re-run misses its
     # committed lengths by up to 4.7e-3 (2 of 64 beyond 3e-3).  Same bar for the engine: the typical curve far inside

@@ -150,20 +150,26 @@ def test_results_do_not_depend_on_sharding_or_chunking(vlg):
     assert torch.equal(ch.omega, full.omega) and torch.equal(e2, e_full)
 
 
-def test_single_decoder_path(vlg):
-    """BASELINE config 2: deterministic energy, 6 steps, then the poly-line length."""
+@pytest.mark.parametrize("prec", ["fp32", "f16x3"])
+def test_single_decoder_path(vlg, prec):
+    """BASELINE config 2: deterministic energy, 6 steps, then the poly-line length.  The 3-term tensor-core mode holds
+    the same bound as the fp32 kernel here (the single-term modes cannot: 11-bit operands, SURVEY hard part 1)."""
     g = Hh.load("single_seed123")
     model = make_model(vlg, g)
     dec = make_decoders(vlg, g, 1)
     t = torch.linspace(0, 1, 2000, device="cuda")
-    E0 = vlg.compute_energy(model, dec, t).cpu().numpy()
+    E0 = vlg.compute_energy(model, dec, t, precision=prec).cpu().numpy()
     # sums of tiny differences of large numbers: fp32 noise of the reference itself is ~1e-4 here
-    assert np.abs(E0 / g["energy_f64"][0] - 1).max() < 5e-4
+    e0 = np.abs(E0 / g["energy_f64"][0] - 1).max()
+    assert e0 < 5e-4
     S = int(g["steps"])
-    _, trace = vlg.optimize_splines(model, dec, t, S, M=1, precision="fp32", return_trace=True)
-    assert np.abs(trace.cpu().numpy() / g["energy_f64"] - 1).max() < 5e-4
-    L = vlg.compute_geodesic_lengths(model, dec, t).cpu().numpy()
-    assert np.abs(L / g["length_f64"] - 1).max() < 2e-4
+    _, trace = vlg.optimize_splines(model, dec, t, S, M=1, precision=prec, return_trace=True)
+    et = np.abs(trace.cpu().numpy() / g["energy_f64"] - 1).max()
+    assert et < 5e-4
+    L = vlg.compute_geodesic_lengths(model, dec, t, precision=prec).cpu().numpy()
+    el = np.abs(L / g["length_f64"] - 1).max()
+    print(f"\nsingle decoder [{prec}]: energy {e0:.1e}, {S}-step energies {et:.1e}, poly-line length {el:.1e} (rel. to fp64)")
+    assert el < 2e-4
 
 
 def test_std_field(vlg):
