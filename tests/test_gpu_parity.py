@@ -402,12 +402,12 @@ def test_final_length_after_150_steps(vlg, prec, tol):
 
 @pytest.mark.parametrize("T,N,K,M,n_poly", [(2, 1, 1, 1, 1), (3, 2, 2, 2, 2), (128, 3, 3, 2, 4), (255, 2, 5, 1, 8),
                                            (256, 1, 16, 2, 4), (257, 2, 4, 2, 4), (600, 3, 1, 1, 4), (513, 150, 7, 2, 4),
-                                           (300, 3, 6, 3, 4), (700, 2, 10, 4, 4), (130, 2, 3, 4, 2)])
+                                           (300, 3, 6, 3, 4), (700, 2, 10, 4, 4), (130, 2, 3, 4, 2), (256, 9, 100, 2, 8)])
 @pytest.mark.parametrize("tc", TC_PRECISIONS)
 def test_tf32_edge_shapes_against_fp32_kernel(vlg, T, N, K, M, n_poly, tc):
     """Window boundaries (255/256/257 points), a decoder drawn by more than 128 points of a window
     (K=1: two 128-row items per window), a single segment, more curves than SMs (persistent CTAs
-    walk several curves), K up to 16, more than two MC samples (the tensor-core kernel works through them in blocks
+    walk several curves), K up to 100, more than two MC samples (the tensor-core kernel works through them in blocks
     of two; the reference exposes --mc-samples freely, src/optimize.py:232).  Compared against the fp32 kernel on
     identical draws."""
     rng = np.random.default_rng(T * 131 + K)

@@ -146,7 +146,7 @@ def _prep_draws(draws, N: int, steps: int, M: int, T: int, device, K_active: int
     return d.to(device=device, dtype=torch.uint8).permute(4, 0, 1, 2, 3).contiguous()
 
 
-TC_MAX_M, TC_MAX_K = 2, 64   # tensor-core kernel (csrc/vlg_tc.cu): MC samples per block, decoder limit
+TC_MAX_M, TC_MAX_K = 2, 128   # tensor-core kernel (csrc/vlg_tc.cu): MC samples per block, decoder limit
 
 # The ONE default arithmetic of the package, the drop-in CLIs (src/optimize.py, src/eval.py) and bench.py.
 DEFAULT_PRECISION = "f16x3"
@@ -154,7 +154,7 @@ DEFAULT_PRECISION = "f16x3"
 
 def _resolve_precision(precision: Optional[str], decoders, M: int) -> int:
     """None -> DEFAULT_PRECISION.  Tensor-core precisions fall back to the fp32 CUDA-core kernel for shapes
-    the tensor-core kernel is not built for (more than 64 decoders; any number of MC samples is fine: the kernel
+    the tensor-core kernel is not built for (more than 128 decoders; any number of MC samples is fine: the kernel
     works through them in blocks of two); the single-term
     ones ('tf32', 'f16': 11-bit operands) also for a single active decoder, where they cannot resolve the tiny
     adjacent-point differences (SURVEY hard part 1; 'f16x3' can).  Still a GPU kernel -- there is no CPU

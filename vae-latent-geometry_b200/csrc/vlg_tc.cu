@@ -108,7 +108,7 @@ constexpr int TC_MAX_WG = 2048;       // points per window when it holds several
 constexpr int TC_MAX_G = 8;           // curves per window (XL2 kernels)
 constexpr int OM_STRIDE = 6 * MAX_KB + 2;   // per-curve omega | adam m | adam v
 constexpr int TC_MAX_M = 2;           // MC samples per block (any number of samples: blocks of two)
-constexpr int TC_MAX_K = 64;          // decoders
+constexpr int TC_MAX_K = 128;         // decoders
 constexpr int MAX_ITEMS = TC_MAX_K + 2 * TC_MAX_M * TC_MAX_WG / 128 + 8;  // sum_k ceil(n_k/128) <= K + 2*M*W/128
 
 // the four tensor-core GEMMs of one decoder
