@@ -3,7 +3,7 @@ import sys, ctypes
 sys.path.insert(0, ".")
 import torch, vlg_b200
 from vlg_b200 import _lib
-lib = _lib.load()
+vlg_b200.build.build_selftest(); lib = _lib.load_selftest()
 fn = lib.vlg_selftest_mma_rate
 fn.restype = ctypes.c_int
 fn.argtypes = [ctypes.c_int] * 6 + [ctypes.c_void_p, ctypes.c_void_p]

@@ -1135,6 +1135,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
               if (lane == 0) s.red[320 + jc * 32 + ew] = e;
             }
             named_bar(3, EPI_THREADS);  // the differences are read by other threads below
+            if (xl2) PHW(20);
             // (2) [only when the differences live in the workspace, xl2: from shared memory the backward items build
             // their dE/dx rows themselves -- inside an item the other chain hides the latency, a CTA-wide pass cannot;
             // measured 411 k vs 349 k spline-steps/s on the headline shape.]  One task = (item, row, 8 output columns): G = (2/M) * [sum over the segments whose RIGHT end is this
@@ -1145,7 +1146,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
             const int ntask = xl2 ? nitems * 1024 : 0;
             const float gsc = F16 ? coefm * F16_GRAD_SCALE : coefm;
             for (int t0 = t512; t0 < ntask; t0 += EPI_THREADS) {
-              const int it = t0 >> 10, c = (t0 >> 7) & 7, r = t0 & 127;
+              // eight consecutive threads = the eight 32-byte chunks of ONE row: a warp gathers four whole rows (a few
+              // 128-byte lines) instead of one sector from each of 32 rows
+              const int it = t0 >> 10, r = (t0 >> 3) & 127, c = t0 & 7;
               const int k = ctl->item[it] & 0xFF, q0 = (ctl->item[it] >> 8) * 128;
               if (q0 + r >= s.cnt[k]) continue;
               const int pt = s.rows[s.roff[k] + q0 + r];
@@ -1209,6 +1212,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
               }
             }
             if (xl2) fence_proxy_async_all();   // the tiles are read by the TMA engine (async proxy)
+            if (xl2) PHW(21);
           } else {
             // forward-only kernel (also reports the polyline length, a sum of per-segment norms): 16 lanes
             // per (m, segment) entry, one 16-byte piece each; six entries per lane in flight.
