@@ -91,6 +91,9 @@ namespace {
 
 using namespace tc;
 
+#ifndef VLG_TC_TILE_TB
+#define VLG_TC_TILE_TB 4              // dE/dx tile pass (multi-curve windows): tasks in flight per thread
+#endif
 #ifndef VLG_TC_DUAL_ISSUE
 #define VLG_TC_DUAL_ISSUE 0           // 1: one MMA issuer warp per chain (see the issuer)
 #endif
@@ -1145,70 +1148,92 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
             // operand from shared memory: no per-item dE/dx build, no epilogue round trip in front of B3.
             const int ntask = xl2 ? nitems * 1024 : 0;
             const float gsc = F16 ? coefm * F16_GRAD_SCALE : coefm;
-            for (int t0 = t512; t0 < ntask; t0 += EPI_THREADS) {
-              // eight consecutive threads = the eight 32-byte chunks of ONE row: a warp gathers four whole rows (a few
-              // 128-byte lines) instead of one sector from each of 32 rows
-              const int it = t0 >> 10, r = (t0 >> 3) & 127, c = t0 & 7;
-              const int k = ctl->item[it] & 0xFF, q0 = (ctl->item[it] >> 8) * 128;
-              if (q0 + r >= s.cnt[k]) continue;
-              const int pt = s.rows[s.roff[k] + q0 + r];
-              float g[8];
+            // Eight consecutive threads = the eight 32-byte chunks of ONE row: a warp gathers four whole rows (a few
+            // 128-byte lines) instead of one sector from each of 32 rows.  The gathers come from L2 -- or HBM: with
+            // several curves per window the per-CTA buffers of a full grid exceed L2 -- so TB tasks per thread are in
+            // flight: first the row lookups and the loads of each task's first matching slot (almost always the only
+            // one), then the arithmetic; further slots of a task are fetched one after the other (rare).  Same order
+            // of additions as the in-item build: slot order (sample 0: right end, left end; sample 1: right end, left end).
+            constexpr int TB = VLG_TC_TILE_TB;
+            for (int tb = t512; tb < ntask; tb += TB * EPI_THREADS) {
+              float4 f0[TB], f1[TB];
+              int ptv[TB];
+              uint32_t mkv[TB];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) g[j] = 0.f;
-              if (c < 7) {
-                const bool wide = c < 6;   // chunk 6 = columns 48..51 (+ zero padding up to 55)
-                float4 dd[2 * TC_MAX_M][2];
-                bool on[2 * TC_MAX_M];
-                const uint32_t eq4 = slot_match(s.sel, pt, k);
-#pragma unroll
-                for (int m = 0; m < TC_MAX_M; ++m) {
-                  on[2 * m] = (eq4 >> (16 * m + 8)) & 1u;   // right end of segment pt-1
-                  on[2 * m + 1] = (eq4 >> (16 * m)) & 1u;   // left end of segment pt
-                }
-#pragma unroll
-                for (int j = 0; j < 2 * TC_MAX_M; ++j) {      // all loads first (L2 latency when xl2)
-                  const float* src = X1 + ptrdiff_t((j >> 1) * W + pt - 1 + (j & 1)) * XD_STRIDE + 8 * c;   // dereferenced only if on[j]
-                  dd[j][0] = dd[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-                  if (on[j]) {
-                    if (xl2) {
-                      dd[j][0] = __ldcg(reinterpret_cast<const float4*>(src));
-                      if (wide) dd[j][1] = __ldcg(reinterpret_cast<const float4*>(src) + 1);
-                    } else {
-                      dd[j][0] = *reinterpret_cast<const float4*>(src);
-                      if (wide) dd[j][1] = *(reinterpret_cast<const float4*>(src) + 1);
+              for (int u = 0; u < TB; ++u) {
+                const int t0 = tb + u * EPI_THREADS;
+                ptv[u] = -1;
+                mkv[u] = 0u;
+                f0[u] = f1[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (t0 < ntask) {
+                  const int it = t0 >> 10, r = (t0 >> 3) & 127, c = t0 & 7;
+                  const int k = ctl->item[it] & 0xFF, q0 = (ctl->item[it] >> 8) * 128;
+                  if (q0 + r < s.cnt[k]) {
+                    const int pt = s.rows[s.roff[k] + q0 + r];
+                    ptv[u] = pt;
+                    if (c < 7) {   // chunk 7 = zero padding (columns 56..63)
+                      const uint32_t eq4 = slot_match(s.sel, pt, k);
+                      // bit j: slot j in the order right end of segment pt-1 (sample 0), left end of segment pt (sample 0), ...
+                      const uint32_t mk = ((eq4 >> 8) & 1u) | ((eq4 << 1) & 2u) | ((eq4 >> 22) & 4u) | ((eq4 >> 13) & 8u);
+                      mkv[u] = mk;
+                      if (mk) {
+                        const int jj = __ffs(int(mk)) - 1;
+                        const float4* src = reinterpret_cast<const float4*>(X1 + ptrdiff_t((jj >> 1) * W + pt - 1 + (jj & 1)) * XD_STRIDE + 8 * c);
+                        f0[u] = xl2 ? __ldcg(src) : *src;
+                        if (c < 6) f1[u] = xl2 ? __ldcg(src + 1) : *(src + 1);   // chunk 6 = columns 48..51 (+ zero padding up to 55)
+                      }
                     }
                   }
                 }
-#pragma unroll
-                for (int j = 0; j < 2 * TC_MAX_M; ++j) {
-                  const float sg = (j & 1) ? -1.f : 1.f;
-                  g[0] = fmaf(sg, dd[j][0].x, g[0]); g[1] = fmaf(sg, dd[j][0].y, g[1]);
-                  g[2] = fmaf(sg, dd[j][0].z, g[2]); g[3] = fmaf(sg, dd[j][0].w, g[3]);
-                  g[4] = fmaf(sg, dd[j][1].x, g[4]); g[5] = fmaf(sg, dd[j][1].y, g[5]);
-                  g[6] = fmaf(sg, dd[j][1].z, g[6]); g[7] = fmaf(sg, dd[j][1].w, g[7]);
-                }
               }
 #pragma unroll
-              for (int j = 0; j < 8; ++j) g[j] *= gsc;
-              unsigned char* tile = Gt + size_t(it) * GT_BYTES;
-              if (F16) {
-                uint4 hi, lo;
-                if (X3) {
-                  pack_hilo_h2(g[0], g[1], hi.x, lo.x); pack_hilo_h2(g[2], g[3], hi.y, lo.y);
-                  pack_hilo_h2(g[4], g[5], hi.z, lo.z); pack_hilo_h2(g[6], g[7], hi.w, lo.w);
-                  *reinterpret_cast<uint4*>(tile + 16384 + (c * 128 + r) * 16) = lo;
-                } else {
-                  hi = make_uint4(pack_h2(g[0], g[1]), pack_h2(g[2], g[3]), pack_h2(g[4], g[5]), pack_h2(g[6], g[7]));
+              for (int u = 0; u < TB; ++u) {
+                if (ptv[u] < 0) continue;
+                const int t0 = tb + u * EPI_THREADS;
+                const int it = t0 >> 10, r = (t0 >> 3) & 127, c = t0 & 7;
+                const int pt = ptv[u];
+                float g[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) g[q] = 0.f;
+                uint32_t mk = mkv[u];
+                float4 a0 = f0[u], a1 = f1[u];
+                while (mk) {
+                  const int jj = __ffs(int(mk)) - 1;
+                  mk &= mk - 1u;
+                  const float sg = (jj & 1) ? -1.f : 1.f;
+                  g[0] = fmaf(sg, a0.x, g[0]); g[1] = fmaf(sg, a0.y, g[1]);
+                  g[2] = fmaf(sg, a0.z, g[2]); g[3] = fmaf(sg, a0.w, g[3]);
+                  g[4] = fmaf(sg, a1.x, g[4]); g[5] = fmaf(sg, a1.y, g[5]);
+                  g[6] = fmaf(sg, a1.z, g[6]); g[7] = fmaf(sg, a1.w, g[7]);
+                  if (mk) {   // a further slot of this row holds the same decoder
+                    const int jn = __ffs(int(mk)) - 1;
+                    const float4* src = reinterpret_cast<const float4*>(X1 + ptrdiff_t((jn >> 1) * W + pt - 1 + (jn & 1)) * XD_STRIDE + 8 * c);
+                    a0 = xl2 ? __ldcg(src) : *src;
+                    a1 = c < 6 ? (xl2 ? __ldcg(src + 1) : *(src + 1)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                  }
                 }
-                *reinterpret_cast<uint4*>(tile + (c * 128 + r) * 16) = hi;
-              } else {
-                uint4 v0, v1;
-                v0 = make_uint4(tf32_round_bits(__float_as_uint(g[0])), tf32_round_bits(__float_as_uint(g[1])),
-                                tf32_round_bits(__float_as_uint(g[2])), tf32_round_bits(__float_as_uint(g[3])));
-                v1 = make_uint4(tf32_round_bits(__float_as_uint(g[4])), tf32_round_bits(__float_as_uint(g[5])),
-                                tf32_round_bits(__float_as_uint(g[6])), tf32_round_bits(__float_as_uint(g[7])));
-                *reinterpret_cast<uint4*>(tile + ((2 * c) * 128 + r) * 16) = v0;
-                *reinterpret_cast<uint4*>(tile + ((2 * c + 1) * 128 + r) * 16) = v1;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) g[q] *= gsc;
+                unsigned char* tile = Gt + size_t(it) * GT_BYTES;
+                if (F16) {
+                  uint4 hi, lo;
+                  if (X3) {
+                    pack_hilo_h2(g[0], g[1], hi.x, lo.x); pack_hilo_h2(g[2], g[3], hi.y, lo.y);
+                    pack_hilo_h2(g[4], g[5], hi.z, lo.z); pack_hilo_h2(g[6], g[7], hi.w, lo.w);
+                    *reinterpret_cast<uint4*>(tile + 16384 + (c * 128 + r) * 16) = lo;
+                  } else {
+                    hi = make_uint4(pack_h2(g[0], g[1]), pack_h2(g[2], g[3]), pack_h2(g[4], g[5]), pack_h2(g[6], g[7]));
+                  }
+                  *reinterpret_cast<uint4*>(tile + (c * 128 + r) * 16) = hi;
+                } else {
+                  uint4 v0, v1;
+                  v0 = make_uint4(tf32_round_bits(__float_as_uint(g[0])), tf32_round_bits(__float_as_uint(g[1])),
+                                  tf32_round_bits(__float_as_uint(g[2])), tf32_round_bits(__float_as_uint(g[3])));
+                  v1 = make_uint4(tf32_round_bits(__float_as_uint(g[4])), tf32_round_bits(__float_as_uint(g[5])),
+                                  tf32_round_bits(__float_as_uint(g[6])), tf32_round_bits(__float_as_uint(g[7])));
+                  *reinterpret_cast<uint4*>(tile + ((2 * c) * 128 + r) * 16) = v0;
+                  *reinterpret_cast<uint4*>(tile + ((2 * c + 1) * 128 + r) * 16) = v1;
+                }
               }
             }
             if (xl2) fence_proxy_async_all();   // the tiles are read by the TMA engine (async proxy)
