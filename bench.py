@@ -49,19 +49,21 @@ M_MC = 2
 FLOP_PER_POINT_DECODER = 92160  # fwd + input-grad bwd of 2->128->128->50
 # tensor FLOPs of ONE executed 128-row item (four GEMMs: 128x128x128, 128x64x128, 128x128x64, 128x128x128)
 FLOP_PER_ITEM = 2 * 128 * (128 * 128 + 64 * 128 + 128 * 64 + 128 * 128)
-MMAS_PER_ITEM = {"f16": 28, "f16x3": 84, "tf32": 56}   # M=128 instructions; 63-69 cycles each
-MMA_TERMS = {"f16": 1, "f16x3": 3, "tf32": 1}
+MMAS_PER_ITEM = {"f16": 28, "f16x3": 84, "f16x3f": 60, "tf32": 56}   # M=128 instructions; 63-69 cycles each
+MMA_TERMS = {"f16": 1, "f16x3": 3, "f16x3f": 60.0 / 28.0, "tf32": 1}
 METRIC = "spline-steps/sec, 8778-pair 10-decoder eVAE energy opt"
 # arithmetic of the two 128-wide decoder layers (layer 1, the energy, the spline and Adam are fp32 everywhere)
 PRECISION_NOTE = {
     "f16": "f16: tcgen05 kind::f16, fp16 operands (11-bit significand, as TF32), fp32 accumulate; <=1e-3 rel. on lengths",
     "f16x3": "f16x3: tcgen05 kind::f16, hi+lo fp16 operands, 3 MMAs per product, fp32 accumulate; fp32-grade (2e-6 rel. per-step energy)",
+    "f16x3f": "f16x3f: f16x3 in the forward GEMMs (energies fp32-grade), single-term fp16 operands in the backward GEMMs",
     "tf32": "tf32: tcgen05 kind::tf32, fp32 accumulate; <=1e-3 rel. on lengths",
     "fp32": "fp32: CUDA-core FFMA; <=1e-4 rel. per-step energy",
 }
 KERNEL_NAME = {"f16": "tc_curve_kernel<true, FMT_F16>", "f16x3": "tc_curve_kernel<true, FMT_F16X3>",
+               "f16x3f": "tc_curve_kernel<true, FMT_F16X3F>",
                "tf32": "tc_curve_kernel<true, FMT_TF32>", "fp32": "simt_curve_kernel<true>"}
-DTYPE = {"f16": "f16", "f16x3": "f16x3", "tf32": "tf32", "fp32": "f32"}
+DTYPE = {"f16": "f16", "f16x3": "f16x3", "f16x3f": "f16x3f", "tf32": "tf32", "fp32": "f32"}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -323,6 +325,8 @@ def run_gpu_arm(args):
     torch.cuda.set_device(dev)
     vlg_b200.build.build()
     precision = args.precision or vlg_b200.DEFAULT_PRECISION
+    if args.config == 2 and precision in ("f16", "tf32", "f16x3f") and not args.precision:
+        precision = "f16x3"     # the single-decoder drop-in's default
     if args.config == 2 and precision in ("f16", "tf32"):
         precision = "f16x3"     # 11-bit operands cannot resolve a single decoder's adjacent-point differences
 
@@ -432,7 +436,7 @@ def run_gpu_arm(args):
     # ---- secondary entries: the other arithmetic modes on the same workload (1 GPU runs only) ----
     other = {}
     if world == 1 and not args.no_other:
-        for prec in ("f16", "f16x3", "tf32", "fp32"):
+        for prec in ("f16", "f16x3", "f16x3f", "tf32", "fp32"):
             if prec == precision or (K == 1 and prec in ("f16", "tf32")):
                 continue
             ns = args.steps if prec != "fp32" else max(1, min(args.steps, 2))
@@ -518,7 +522,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="vlg", choices=["vlg", "reference"])
-    ap.add_argument("--precision", default=None, choices=["f16", "f16x3", "tf32", "fp32"],
+    ap.add_argument("--precision", default=None, choices=["f16", "f16x3", "f16x3f", "tf32", "fp32"],
                     help="default: vlg_b200.DEFAULT_PRECISION (the one default of the package and the CLIs)")
     ap.add_argument("--config", type=int, default=3, choices=[2, 3, 5], help="BASELINE.json configuration")
     ap.add_argument("--chunk", type=int, default=50, help="Adam steps per kernel launch")

@@ -64,9 +64,11 @@ enum {
                                hi*hi + lo*hi + hi*lo in the fp32 accumulator: fp32-grade (measured 2e-6
                                relative per-step energy), 5-6x the speed of the CUDA-core kernel       */
   VLG_PRECISION_TF32X3 = 2, /* former name of the same slot */
-  VLG_PRECISION_F16 = 3     /* tcgen05.mma kind::f16: fp16 operands (11-bit significand, as TF32; backward
+  VLG_PRECISION_F16 = 3,    /* tcgen05.mma kind::f16: fp16 operands (11-bit significand, as TF32; backward
                                quantities pre-scaled by 2^6), fp32 accumulate in TMEM: half the tensor-pipe
                                time and weight traffic of TF32 for the same <=1e-3 length tolerance     */
+  VLG_PRECISION_F16X3F = 4  /* 3-term split in the forward GEMMs (energies and lengths fp32-grade, as F16X3),
+                               single-term fp16 operands in the backward GEMMs (gradient to ~2.5e-4 relative) */
 };
 
 const char* vlg_error_string(int code);

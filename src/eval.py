@@ -100,7 +100,7 @@ def main():
     parser.add_argument("--pair-count", type=int, default=133)
     parser.add_argument("--seed", type=int)
     parser.add_argument("--seeds", nargs="*", type=int, default=[12, 123])
-    parser.add_argument("--precision", type=str, default=vlg_b200.DEFAULT_PRECISION, choices=["f16", "f16x3", "tf32", "fp32"])
+    parser.add_argument("--precision", type=str, default=vlg_b200.DEFAULT_PRECISION, choices=["f16", "f16x3", "f16x3f", "tf32", "fp32"])
     args = parser.parse_args()
     plot_dir = Path("experiment/plots")
     plot_dir.mkdir(parents=True, exist_ok=True)

@@ -100,10 +100,10 @@ if __name__ == "__main__":
     parser.add_argument("--steps", type=int, default=100)
     parser.add_argument("--batch-size", type=int, default=200, help="accepted for compatibility; ignored")
     parser.add_argument("--mc-samples", type=int, default=2)
-    parser.add_argument("--precision", type=str, default=vlg_b200.DEFAULT_PRECISION, choices=["f16", "f16x3", "tf32", "fp32"],
-                        help="tcgen05 tensor-core kernel with 3-term fp16 (f16x3: fp32-grade), fp16 or TF32 "
-                             "operands (<=1e-3 on lengths, faster; fp16 operands must stay below 65504), "
-                             "or fp32: the CUDA-core kernel")
+    parser.add_argument("--precision", type=str, default=vlg_b200.DEFAULT_PRECISION, choices=["f16", "f16x3", "f16x3f", "tf32", "fp32"],
+                        help="tcgen05 tensor-core kernel: f16x3f (default: 3-term fp16 forward = fp32-grade energies, "
+                             "single-term backward), f16x3 (all GEMMs 3-term: fp32-grade), f16 or tf32 operands "
+                             "(<=1e-3 on lengths, fastest; fp16 operands must stay below 65504), or fp32: the CUDA-core kernel")
     parser.add_argument("--seed", type=int, default=0, help="seed of the decoder-pair draws")
     args = parser.parse_args()
     main(model_path=args.model_path, spline_path=args.spline_path, init_type=args.init_type, pair_count=args.pair_count,

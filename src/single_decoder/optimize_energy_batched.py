@@ -22,7 +22,7 @@ import vlg_b200
 from vlg_b200 import formats, sharding
 
 
-def main(seed, pairfile, batch_size=250, steps=500, precision=None, artifact_dir="src/artifacts"):
+def main(seed, pairfile, batch_size=250, steps=500, precision="f16x3", artifact_dir="src/artifacts"):
     pair_tag = Path(pairfile).stem.replace("selected_pairs_", "")
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -77,8 +77,8 @@ if __name__ == "__main__":
     parser.add_argument("--seed", type=int, required=True)
     parser.add_argument("--pairfile", type=str, required=True, help="selected_pairs_*.json")
     parser.add_argument("--steps", type=int, default=500)
-    parser.add_argument("--precision", type=str, default=None, choices=["fp32", "f16x3"],
-                        help="default: the package default, f16x3 = 3-term split on the tensor pipe (fp32-grade; 4.8x the "
+    parser.add_argument("--precision", type=str, default="f16x3", choices=["fp32", "f16x3", "f16x3f"],
+                        help="default: f16x3 = 3-term split on the tensor pipe (fp32-grade; 4.8x the "
                              "fp32 CUDA-core kernel on this job); fp32: CUDA-core kernel.  The single-term tensor-core "
                              "modes are not offered: 11-bit operands cannot resolve a single decoder's adjacent-point "
                              "differences")

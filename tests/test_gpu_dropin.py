@@ -159,7 +159,7 @@ def test_cov_shrinks_with_more_decoders_on_the_committed_checkpoints(built_lib):
     assert cov[10] < cov[1]
 
 
-@pytest.mark.parametrize("prec", ["fp32", "f16x3"])
+@pytest.mark.parametrize("prec", ["fp32", "f16x3", "f16x3f"])
 def test_single_decoder_dropin_reproduces_committed_lengths(tmp_path, built_lib, prec):
     """BASELINE config 2 through the drop-in CLI module: 64 curves of the reference's committed input
     (src/artifacts/spline_batch_seed123.pt), 500 steps, against the length_geodesic the reference committed in

@@ -150,7 +150,7 @@ def test_results_do_not_depend_on_sharding_or_chunking(vlg):
     assert torch.equal(ch.omega, full.omega) and torch.equal(e2, e_full)
 
 
-@pytest.mark.parametrize("prec", ["fp32", "f16x3"])
+@pytest.mark.parametrize("prec", ["fp32", "f16x3", "f16x3f"])
 def test_single_decoder_path(vlg, prec):
     """BASELINE config 2: deterministic energy, 6 steps, then the poly-line length.  The 3-term tensor-core mode holds
     the same bound as the fp32 kernel here (the single-term modes cannot: 11-bit operands, SURVEY hard part 1)."""
@@ -340,7 +340,7 @@ def test_split_row_lists_are_deterministic(vlg, tc):
 # on energies.
 # ---------------------------------------------------------------------------------------------
 TF32_LENGTH_TOL = 1e-3
-TC_PRECISIONS = ["tf32", "f16", "f16x3"]
+TC_PRECISIONS = ["tf32", "f16", "f16x3", "f16x3f"]
 
 
 @pytest.mark.parametrize("tag", ["ens_seed12_euclid", "ens_seed12_entropy", "ens_seed12_cov_k3", "synth_np8_T256",
@@ -380,7 +380,7 @@ def test_tf32_forward_energy_full_size(vlg, tc):
     assert np.abs(np.sqrt(etc / e32) - 1).max() < TF32_LENGTH_TOL
 
 
-@pytest.mark.parametrize("prec,tol", [("fp32", 2e-5), ("tf32", TF32_LENGTH_TOL), ("f16", TF32_LENGTH_TOL), ("f16x3", 2e-5)])
+@pytest.mark.parametrize("prec,tol", [("fp32", 2e-5), ("tf32", TF32_LENGTH_TOL), ("f16", TF32_LENGTH_TOL), ("f16x3", 2e-5), ("f16x3f", 1e-4)])
 def test_final_length_after_150_steps(vlg, prec, tol):
     """Long horizon (free-running, not teacher-forced): final sqrt(E) against the reference's own
     fp64 run with the same recorded draws.  The reference's fp32-vs-fp64 gap is printed beside it."""
@@ -604,7 +604,7 @@ def test_full_config1_1000_steps_final_lengths(vlg, prec, tol):
     assert np.abs(model.omega.cpu().numpy() - g["omega_f64"]).max() < 5e-2
 
 
-@pytest.mark.parametrize("prec", ["f16", "f16x3", "tf32"])
+@pytest.mark.parametrize("prec", ["f16", "f16x3", "f16x3f", "tf32"])
 def test_full_pair_list_sharding_and_modes_agree(vlg, prec):
     """BASELINE config 3 at its full width (8778 pairs, K=10, M=2, T=2000), size-independent properties:
     the 8-way shard of the pair list reproduces the single-launch result bit for bit (the work queue hands
@@ -716,7 +716,7 @@ def _run_config3_curves(vlg, ids, prec, steps=1000):
     return out
 
 
-@pytest.mark.parametrize("prec", ["fp32", "f16x3", "f16", "tf32"])
+@pytest.mark.parametrize("prec", ["fp32", "f16x3", "f16x3f", "f16", "tf32"])
 def test_config3_final_lengths_against_reference_fp64(vlg, prec):
     """north_star: <= 1e-3 relative final geodesic length.  The golden holds 64 curves of the benchmarked job after
     1000 free-running Adam steps of the reference's own loop in fp64 and in fp32: the first 49 curves (an unselected
@@ -747,8 +747,9 @@ def test_config3_final_lengths_against_reference_fp64(vlg, prec):
     err32 = np.abs(got / g["final_length_f32"].astype(np.float64) - 1)
     print(f"   against the reference's fp32 run: median {np.median(err32):.1e}, unselected max {err32[plain].max():.1e}, overall max {err32.max():.1e}")
     assert np.isfinite(got).all()
-    if prec in ("fp32", "f16x3"):
-        assert err[plain].max() <= 1e-3 and np.median(err) <= 1e-5
+    if prec in ("fp32", "f16x3", "f16x3f"):
+        # (f16x3f: energies fp32-grade, gradient GEMMs on 11-bit operands -- the trajectories differ a little more)
+        assert err[plain].max() <= 1e-3 and np.median(err) <= (5e-5 if prec == "f16x3f" else 1e-5)
         assert (err > 1e-3).sum() <= (gap > 1e-3).sum() + 2
         assert err.max() <= 2 * gap.max()
     else:

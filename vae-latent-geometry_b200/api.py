@@ -148,8 +148,13 @@ def _prep_draws(draws, N: int, steps: int, M: int, T: int, device, K_active: int
 
 TC_MAX_M, TC_MAX_K = 2, 128   # tensor-core kernel (csrc/vlg_tc.cu): MC samples per block, decoder limit
 
-# The ONE default arithmetic of the package, the drop-in CLIs (src/optimize.py, src/eval.py) and bench.py.
-DEFAULT_PRECISION = "f16x3"
+# The ONE default arithmetic of the package, the drop-in CLIs (src/optimize.py, src/eval.py) and bench.py: the
+# 3-term fp16 split in the forward GEMMs -- energies and lengths of a given curve are fp32-grade (1e-6) -- and
+# single-term fp16 operands in the backward GEMMs (gradient to ~2.5e-4).  After 1000 free-running Adam steps on the
+# benchmarked curves: median 1.0e-5, max 1.3e-4 against the reference's fp64 run where its own fp32 run has
+# 8.3e-7 / 1.0e-4 (north-star bound 1e-3; tests/golden/config3_synth_1000.npz).  "f16x3" (all GEMMs 3-term) is the
+# fp32-grade option, "f16" / "tf32" the 11-bit ones, "fp32" the CUDA-core kernel.
+DEFAULT_PRECISION = "f16x3f"
 
 
 def _resolve_precision(precision: Optional[str], decoders, M: int) -> int:
@@ -273,10 +278,10 @@ def compute_geodesic_lengths(spline: GeodesicSplineBatch, decoder: DecoderEnsemb
 
 
 def optimize_single_decoder(model: GeodesicSplineBatch, decoder: DecoderEnsemble, t_vals: torch.Tensor,
-                            steps: int = 500, lr: float = 1e-3, precision: Optional[str] = None):
+                            steps: int = 500, lr: float = 1e-3, precision: Optional[str] = "f16x3"):
     """The loop of src/single_decoder/optimize_energy_batched.py:95-102 (deterministic energy).
-    With a single active decoder every counter draw is 0, so no draw tensor is needed.  precision None = the
-    package default (f16x3: fp32-grade on the tensor pipe; measured on the 64-curve x 500-step golden: median 1.9e-4,
+    With a single active decoder every counter draw is 0, so no draw tensor is needed.  Default: f16x3 (all GEMMs
+    3-term, fp32-grade on the tensor pipe; measured on the 64-curve x 500-step golden: median 1.9e-4,
     max 2.7e-3 against the reference's committed lengths, where its own CPU re-run has 1.3e-4 / 4.7e-3)."""
     return optimize_splines(model, decoder[:1], t_vals, steps, M=1, lr=lr, draws=None, precision=precision)
 

@@ -32,7 +32,7 @@ int fill_params(vlg::StepParams* p, const void* packed, int K, int X, int K_acti
   if (!packed || N <= 0 || T < 2 || n_poly < 1 || M < 1 || K_active < 1) return VLG_ERR_INVALID_ARGUMENT;
   // MC samples: the fp32 kernel holds all of them at once (<= MAX_M); the tensor-core kernel walks blocks of two (<= 64)
   if (n_poly > vlg::MAX_NPOLY || M > (precision == VLG_PRECISION_FP32 ? vlg::MAX_M : 64) || K_active > 254) return VLG_ERR_UNSUPPORTED;
-  if (precision < VLG_PRECISION_FP32 || precision > VLG_PRECISION_F16) return VLG_ERR_INVALID_ARGUMENT;
+  if (precision < VLG_PRECISION_FP32 || precision > VLG_PRECISION_F16X3F) return VLG_ERR_INVALID_ARGUMENT;
   if (vlg_packed_decoders_bytes(K, vlg::H, X) == 0 || K_active > K) return VLG_ERR_INVALID_ARGUMENT;
   memset(p, 0, sizeof(*p));
   p->packed = packed;

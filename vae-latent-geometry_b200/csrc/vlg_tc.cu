@@ -14,6 +14,7 @@
 //   FMT_TF32   kind::tf32, operands rounded to TF32 (<= 1e-3 relative on lengths)
 //   FMT_F16    kind::f16, fp16 operands: same 11-bit significand, half the MMAs and weight bytes
 //   FMT_F16X3  kind::f16, every operand as hi + lo fp16 pairs, three MMAs per product: fp32-grade
+//   FMT_F16X3F the same in the forward GEMMs (energies fp32-grade), single-term fp16 in the backward GEMMs
 //
 // ROW COMPACTION.  The MC energy touches, per curve point, only the decoders drawn for the two
 // segments that meet there (<= 2M of K; 3.4 of 10 on average), and the reference's dense
@@ -125,7 +126,7 @@ struct OpInfo {
   int img_lo;    // 3-term mode: float offset of the residual image
 };
 // operand formats of the tensor-core kernel
-constexpr int FMT_TF32 = 0, FMT_F16 = 1, FMT_F16X3 = 2;
+constexpr int FMT_TF32 = 0, FMT_F16 = 1, FMT_F16X3 = 2, FMT_F16X3F = 3;   // X3F: 3-term forward GEMMs, single-term backward GEMMs
 // kind::tf32: activations are fp32 words with TF32-rounded bits, one per TMEM column; an accumulator is
 // overwritten in place by the next layer's operand (X = columns 0..127 of the chain, Y = 128..255).
 // kind::f16 : activations are fp16 pairs, two per column, so an operand takes half the columns of the
@@ -138,7 +139,7 @@ constexpr int FMT_TF32 = 0, FMT_F16 = 1, FMT_F16X3 = 2;
 template <int FMT>
 __device__ __forceinline__ OpInfo op_info(int op) {
   if (FMT != FMT_TF32) {
-    const int d3 = FMT == FMT_F16X3 ? 128 : 64;
+    const int d3 = (FMT == FMT_F16X3 || FMT == FMT_F16X3F) ? 128 : 64;
     switch (op) {
       case 0: return {OFF_W2_H, 2, 128, 4, 0, 128, OFF_W2_HL};     // F2: D2(Y) = A1(X[0:64]) * W2^T
       case 1: return {OFF_W3_H, 1, 64, 8, 0, d3, OFF_W3_HL};       // F3: D3(X[64:128] | Y[0:64]) = A2(X[0:64]) * W3^T
@@ -402,7 +403,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
   const int G = XL2 ? G_ : 1;             // curves per window of this launch: G > 1 = G whole curves (W = G T points)
   const int Wp = W / G;                   // points of one curve in a window
   constexpr bool F16 = FMT != FMT_TF32;   // fp16 operands (one or two terms)
-  constexpr bool X3 = FMT == FMT_F16X3;   // 3-term split
+  constexpr bool X3F = FMT == FMT_F16X3 || FMT == FMT_F16X3F;   // 3-term split in the forward GEMMs (F2, F3)
+  constexpr bool X3B = FMT == FMT_F16X3;                        // ... and in the backward GEMMs (B3, B2)
   constexpr bool DUAL_ISSUE = VLG_TC_DUAL_ISSUE != 0;   // one MMA issuer warp per chain
   extern __shared__ __align__(128) unsigned char smem_raw[];
 #ifdef VLG_TC_STATS
@@ -504,7 +506,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                 // (tf32: 16 KB of each image per half; 3-term: hi half | lo half, 8 KB each, in one stage) -- so
                 // no more than two stages are live at a time and a two-stage ring is enough.
                 const char* gt = reinterpret_cast<const char*>(gtiles) + size_t(i) * GT_BYTES;
-                constexpr int NPAIR = (F16 && !X3) ? 1 : 2;
+                constexpr int NPAIR = (F16 && !X3B) ? 1 : 2;
                 for (int st = 0; st < 2 * NPAIR; ++st) {
                   const int kh = st >> 1;
                   const bool is_g = st & 1;
@@ -515,7 +517,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                   mbar_wait(&emptyc[slot], ph ^ 1);
                   mbar_expect_tx(&fullc[slot], STAGE_BYTES);
                   unsigned char* dst = ringc + slot * STAGE_BYTES;
-                  if (X3) {
+                  if (X3B) {
                     const char* hi = is_g ? gt : src;
                     const char* lo = is_g ? gt + 16384 : src_lo;
                     bulk_g2s(dst, hi + kh * 8192, 8192, &fullc[slot]);
@@ -528,7 +530,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                 continue;
               }
               // 3-term mode: the stages of the main image, then the stages of the residual image
-              for (int st = 0; st < (X3 ? 2 : 1) * oi.nstages; ++st) {
+              for (int st = 0; st < ((phase == 0 ? X3F : X3B) ? 2 : 1) * oi.nstages; ++st) {
                 const char* from = st < oi.nstages ? src + size_t(st) * STAGE_BYTES : src_lo + size_t(st - oi.nstages) * STAGE_BYTES;
                 mbar_wait(&emptyc[slot], ph ^ 1);
                 mbar_expect_tx(&fullc[slot], STAGE_BYTES);
@@ -590,6 +592,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
           // op order inside a window: F2 F3 per item, then B3 B2 per item
           const int optype = (opi[c] < 2 * nitc[c]) ? (opi[c] & 1) : 2 + ((opi[c] - 2 * nitc[c]) & 1);
           const OpInfo oi = op_info<FMT>(optype);
+          const bool x3op = optype < 2 ? X3F : X3B;   // 3-term split of this GEMM
           const uint32_t idesc = F16 ? umma_idesc_f16(oi.n) : umma_idesc_tf32(oi.n, 0);
           const uint32_t chain = tmem + uint32_t(c) * 256u;
           uint64_t* fullc = full + c * MAX_STAGES;
@@ -598,7 +601,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
           if (xl2 && optype == 2) {
             // B3 = dE/dx tile (A, shared memory) x W3 image (B, shared memory); (W, G) stage pairs as the producer
             // queued them.  Both images: K-major, 16-byte core-matrix rows, 128 rows per k-chunk (LBO 2048, SBO 128).
-            constexpr int NPAIR = (F16 && !X3) ? 1 : 2;
+            constexpr int NPAIR = (F16 && !X3B) ? 1 : 2;
             const uint32_t dcol = chain + oi.d_col;
 #pragma unroll
             for (int pr = 0; pr < NPAIR; ++pr) {
@@ -615,7 +618,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                 for (int ks = 0; ks < 4; ++ks)   // K = 8 per MMA: two k-chunks of 4 floats
                   umma_tf32_ss_elect(dcol, umma_smem_desc(gb + uint32_t(ks) * 4096u, 2048u, 128u),
                                      umma_smem_desc(wb + uint32_t(ks) * 4096u, 2048u, 128u), idesc, (pr | ks) ? 1u : 0u, leader);
-              } else if (X3) {
+              } else if (X3B) {
 #pragma unroll
                 for (int term = 0; term < 3; ++term) {   // Ghi Whi, Glo Whi, Ghi Wlo; lo halves sit 8 KB into the stage
                   const uint32_t a_s = gb + (term == 1 ? 8192u : 0u), b_s = wb + (term == 2 ? 8192u : 0u);
@@ -634,18 +637,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
               umma_commit_elect(&emptyc[s_g], leader);
             }
           } else
-          for (int st = 0; st < (X3 ? 2 : 1) * oi.nstages; ++st) {
+          for (int st = 0; st < (x3op ? 2 : 1) * oi.nstages; ++st) {
             if (!mbar_test(&fullc[slot[c]], ph[c])) { STAT_T0(); mbar_wait(&fullc[slot[c]], ph[c]); STAT_ADD(w_full); }
             tc_fence_after();
             const uint32_t sbase = smem_u32(ringc + slot[c] * STAGE_BYTES);
             const int nk = oi.nk;
-            const bool w_lo = X3 && st >= oi.nstages;          // this stage holds residual weights
+            const bool w_lo = x3op && st >= oi.nstages;          // this stage holds residual weights
             const int kst = w_lo ? st - oi.nstages : st;       // which slice of the contraction
             {
               STAT_T0();
               // main weights: main operand (and, 3-term mode, the residual operand 64 columns up);
               // residual weights: main operand only
-              for (int term = 0; term < ((X3 && !w_lo) ? 2 : 1); ++term)
+              for (int term = 0; term < ((x3op && !w_lo) ? 2 : 1); ++term)
                 for (int ks = 0; ks < nk; ++ks) {
                   const uint64_t desc =
                       umma_smem_desc(sbase + uint32_t(ks) * 2u * uint32_t(oi.n) * 16u, uint32_t(oi.n) * 16u, 128u);
@@ -941,7 +944,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                                                  __ffma2_rn(make_float2(wx.x, wx.y), zx2, make_float2(bb.x, bb.y)));
                     const float2 h1 = __ffma2_rn(make_float2(wy.z, wy.w), zy2,
                                                  __ffma2_rn(make_float2(wx.z, wx.w), zx2, make_float2(bb.z, bb.w)));
-                    if (X3) {
+                    if (X3F) {
                       pack_hilo_h2(fmaxf(h0.x, 0.f), fmaxf(h0.y, 0.f), v[j >> 1], vl[j >> 1]);
                       pack_hilo_h2(fmaxf(h1.x, 0.f), fmaxf(h1.y, 0.f), v[(j >> 1) + 1], vl[(j >> 1) + 1]);
                     } else {
@@ -950,7 +953,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                     }
                   }
                   tmem_st16(colX + half * 32 + 16 * hh, v);
-                  if (X3) tmem_st16(colX + 64 + half * 32 + 16 * hh, vl);
+                  if (X3F) tmem_st16(colX + 64 + half * 32 + 16 * hh, vl);
                 }
               }
             } else if (wact) {
@@ -990,7 +993,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
 #pragma unroll
               for (int hh = 0; hh < 2; ++hh) {
                 uint32_t v[32];
-                uint32_t vlo[X3 ? 16 : 1];
+                uint32_t vlo[X3F ? 16 : 1];
                 tmem_ld32_sync(colY + col0 + 32 * hh, v);
                 uint32_t bb = 0;
 #pragma unroll
@@ -998,13 +1001,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                   const float4 b0 = *reinterpret_cast<const float4*>(sw + OFF_B2 + col0 + 32 * hh + j);
                   const float2 p0 = __fadd2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), make_float2(b0.x, b0.y));
                   const float2 p1 = __fadd2_rn(make_float2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])), make_float2(b0.z, b0.w));
-                  if (!(VLG_OPT_MASKH && F16 && !X3)) {
+                  if (!(VLG_OPT_MASKH && F16 && !X3F)) {
                     if (p0.x > 0.f) bb |= 1u << j;
                     if (p0.y > 0.f) bb |= 2u << j;
                     if (p1.x > 0.f) bb |= 4u << j;
                     if (p1.y > 0.f) bb |= 8u << j;
                   }
-                  if (X3) {
+                  if (X3F) {
                     uint32_t a0, a1;
                     pack_hilo_h2(fmaxf(p0.x, 0.f), fmaxf(p0.y, 0.f), a0, vlo[j >> 1]);
                     pack_hilo_h2(fmaxf(p1.x, 0.f), fmaxf(p1.y, 0.f), a1, vlo[(j >> 1) + 1]);
@@ -1028,7 +1031,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                   tmem_st16(colX + half * 32 + 16 * hh, reinterpret_cast<uint32_t(&)[16]>(v));
                 else
                   tmem_st32(colY + col0 + 32 * hh, v);
-                if (X3) tmem_st16(colX + 64 + half * 32 + 16 * hh, reinterpret_cast<uint32_t(&)[16]>(vlo));
+                if (X3F) tmem_st16(colX + 64 + half * 32 + 16 * hh, reinterpret_cast<uint32_t(&)[16]>(vlo));
               }
               if (GRAD && active) *reinterpret_cast<uint2*>(maskws + (it * 128 + row) * 4 + half * 2) = make_uint2(bits[0], bits[1]);
             }
@@ -1043,7 +1046,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
             PH(4); SKEW(18);
             if (wact) {
               uint32_t xv[32];
-              tmem_ld32_sync((X3 ? colY : colX + (F16 ? 64 : 0)) + xc0, xv);
+              tmem_ld32_sync((X3F ? colY : colX + (F16 ? 64 : 0)) + xc0, xv);
               float x[32];
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
@@ -1217,7 +1220,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                 unsigned char* tile = Gt + size_t(it) * GT_BYTES;
                 if (F16) {
                   uint4 hi, lo;
-                  if (X3) {
+                  if (X3B) {
                     pack_hilo_h2(g[0], g[1], hi.x, lo.x); pack_hilo_h2(g[2], g[3], hi.y, lo.y);
                     pack_hilo_h2(g[4], g[5], hi.z, lo.z); pack_hilo_h2(g[6], g[7], hi.w, lo.w);
                     *reinterpret_cast<uint4*>(tile + 16384 + (c * 128 + r) * 16) = lo;
@@ -1341,17 +1344,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                     }
                   }
                   if (F16) {
-                    uint32_t v[16], vl[X3 ? 16 : 1];
+                    uint32_t v[16], vl[X3B ? 16 : 1];
   #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                       const float g0 = (coefm * F16_GRAD_SCALE) * g[2 * j], g1 = (coefm * F16_GRAD_SCALE) * g[2 * j + 1];
-                      if (X3)
+                      if (X3B)
                         pack_hilo_h2(g0, g1, v[j], vl[j]);
                       else
                         v[j] = pack_h2(g0, g1);
                     }
                     tmem_st16(colX + half * 16, v);
-                    if (X3) tmem_st16(colX + 64 + half * 16, reinterpret_cast<uint32_t(&)[16]>(vl));
+                    if (X3B) tmem_st16(colX + 64 + half * 16, reinterpret_cast<uint32_t(&)[16]>(vl));
                   } else {
                     uint32_t v[32];
   #pragma unroll
@@ -1380,10 +1383,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                   tmem_ld32_sync(colY + col0 + 32 * hh, v);
                   const uint32_t mb = hh ? bits.y : bits.x;
                   if (F16) {
-                    uint32_t vl[X3 ? 16 : 1];
+                    uint32_t vl[X3B ? 16 : 1];
 #pragma unroll
                     for (int j = 0; j < 32; j += 2) {
-                      if (VLG_OPT_MASKH && !X3) {
+                      if (VLG_OPT_MASKH && !X3F) {
                         // bits p, 16+p -> 0xFFFF lane masks (no carries: 1 * 0xFFFF, 0x10000 * 0xFFFF)
                         const uint32_t lanes = ((mb >> (j >> 1)) & 0x00010001u) * 0xFFFFu;
                         v[j >> 1] = pack_h2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])) & lanes;
@@ -1391,13 +1394,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                       }
                       const float a0 = ((mb >> j) & 1u) ? __uint_as_float(v[j]) : 0.f;
                       const float a1 = ((mb >> (j + 1)) & 1u) ? __uint_as_float(v[j + 1]) : 0.f;
-                      if (X3)
+                      if (X3B)
                         pack_hilo_h2(a0, a1, v[j >> 1], vl[j >> 1]);
                       else
                         v[j >> 1] = pack_h2(a0, a1);   // j/2 <= j: slot already consumed
                     }
                     tmem_st16(colX + half * 32 + 16 * hh, reinterpret_cast<uint32_t(&)[16]>(v));
-                    if (X3) tmem_st16(colX + 64 + half * 32 + 16 * hh, reinterpret_cast<uint32_t(&)[16]>(vl));
+                    if (X3B) tmem_st16(colX + 64 + half * 32 + 16 * hh, reinterpret_cast<uint32_t(&)[16]>(vl));
                   } else {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = ((mb >> j) & 1u) ? tf32_round_bits(v[j]) : 0u;
@@ -1670,8 +1673,8 @@ extern "C" int vlg_debug_tc_phase(long long* host_out, int n) {
 #endif
 
 cudaError_t launch_tc(const StepParams& p, bool grad, cudaStream_t stream) {
-  if (p.precision < 1 || p.precision > 3) return cudaErrorNotSupported;
-  const int fmt = p.precision == 1 ? FMT_TF32 : p.precision == 3 ? FMT_F16 : FMT_F16X3;
+  if (p.precision < 1 || p.precision > 4) return cudaErrorNotSupported;
+  const int fmt = p.precision == 1 ? FMT_TF32 : p.precision == 3 ? FMT_F16 : p.precision == 4 ? FMT_F16X3F : FMT_F16X3;
   if (p.K > TC_MAX_K || p.M < 1) return cudaErrorNotSupported;
   const int Mc = p.M > TC_MAX_M ? TC_MAX_M : p.M;
   const TcPlan pl = tc_plan(p.T, p.K, Mc, p.dec_base == nullptr);   // per-curve weight sets: one curve per window
@@ -1698,8 +1701,12 @@ cudaError_t launch_tc(const StepParams& p, bool grad, cudaStream_t stream) {
   };
   auto by_fmt = [&](auto grad_c, auto xl2_c) -> cudaError_t {
     constexpr bool G = decltype(grad_c)::value, X = decltype(xl2_c)::value;
-    return fmt == FMT_TF32 ? launch(tc_curve_kernel<G, FMT_TF32, X>)
-           : fmt == FMT_F16 ? launch(tc_curve_kernel<G, FMT_F16, X>) : launch(tc_curve_kernel<G, FMT_F16X3, X>);
+    if (fmt == FMT_TF32) return launch(tc_curve_kernel<G, FMT_TF32, X>);
+    if (fmt == FMT_F16) return launch(tc_curve_kernel<G, FMT_F16, X>);
+    if constexpr (G) {   // forward only: the mixed format IS the 3-term format
+      if (fmt == FMT_F16X3F) return launch(tc_curve_kernel<G, FMT_F16X3F, X>);
+    }
+    return launch(tc_curve_kernel<G, FMT_F16X3, X>);
   };
   using T_ = std::true_type;
   using F_ = std::false_type;

@@ -12,7 +12,7 @@ import torch
 
 from . import _lib
 
-PRECISIONS = {"fp32": 0, "tf32": 1, "f16x3": 2, "tf32x3": 2, "f16": 3}
+PRECISIONS = {"fp32": 0, "tf32": 1, "f16x3": 2, "tf32x3": 2, "f16": 3, "f16x3f": 4}
 
 
 def _chk(x: Optional[torch.Tensor], name: str, dtype=torch.float32, shape=None):
