@@ -7,7 +7,7 @@ import json, subprocess, os
 out = {}
 ncurves = {"3": 8778, "5": 100000}
 for cfg in ("3", "5"):
-    for prec in ("f16x3", "f16"):
+    for prec in ("f16x3f", "f16x3", "f16"):
         rep = f"gpurun_out/r02_tc_{prec}_c{cfg}.ncu-rep"
         if not os.path.exists(rep):
             continue
