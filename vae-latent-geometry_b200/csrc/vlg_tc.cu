@@ -95,6 +95,9 @@ using namespace tc;
 #ifndef VLG_TC_TILE_TB
 #define VLG_TC_TILE_TB 4              // dE/dx tile pass (multi-curve windows): tasks in flight per thread
 #endif
+#ifndef VLG_TC_G_AHEAD
+#define VLG_TC_G_AHEAD 1               // single-term backward: next item's dE/dx rows built under the current B2
+#endif
 #ifndef VLG_TC_DUAL_ISSUE
 #define VLG_TC_DUAL_ISSUE 0           // 1: one MMA issuer warp per chain (see the issuer)
 #endif
@@ -143,7 +146,7 @@ __device__ __forceinline__ OpInfo op_info(int op) {
     switch (op) {
       case 0: return {OFF_W2_H, 2, 128, 4, 0, 128, OFF_W2_HL};     // F2: D2(Y) = A1(X[0:64]) * W2^T
       case 1: return {OFF_W3_H, 1, 64, 8, 0, d3, OFF_W3_HL};       // F3: D3(X[64:128] | Y[0:64]) = A2(X[0:64]) * W3^T
-      case 2: return {OFF_W3T_H, 1, 128, 4, 0, 128, OFF_W3T_HL};   // B3: D4(Y) = G(X[0:32]) * W3
+      case 2: return {OFF_W3T_H, 1, 128, 4, (FMT == FMT_F16X3 || !VLG_TC_G_AHEAD) ? 0 : 64, 128, OFF_W3T_HL};   // B3: D4(Y) = G(X[0:32] | X[64:96]) * W3
       default: return {OFF_W2T_H, 2, 128, 4, 0, 128, OFF_W2T_HL};  // B2: D5(Y) = A4(X[0:64]) * W2
     }
   }
@@ -1294,29 +1297,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
             // point are added in slot order afterwards: the result does not depend on which item / chain / window-mate
             // a row was processed with.  The halves meet through dzx one item later (the chain's next MMA round trip
             // is a barrier between the group's threads).
-            int pend_pt = -1, pend_slot = 0;
-            for (int it = chain_id; it < nitems; it += 2) {
-              const int k = ctl->item[it] & 0xFF, q0 = (ctl->item[it] >> 8) * 128;
-              const bool active = q0 + row < s.cnt[k];
-              const bool wact = q0 + (warp & 3) * 32 < s.cnt[k];
-              const int pt = active ? s.rows[s.roff[k] + q0 + row] : 0;
-              mbar_wait(&sw_full[chain_id * SW_SLOTS + (swj % SW_SLOTS)], (swj / SW_SLOTS) & 1u);
-              if (!F16) named_bar(bar_id, GROUP_THREADS);
-              const float* sw = swbuf + (swj % SW_SLOTS) * 576;
-              ++swj;
-              const float2 z = s.zs[pt];
-              const float2 zx2 = make_float2(z.x, z.x), zy2 = make_float2(z.y, z.y);
-              // mask words for E-B3 (the L2 round trip overlaps the first MMA)
-              uint2 bits = make_uint2(0u, 0u);
-              if (active) bits = *reinterpret_cast<const uint2*>(maskws + (it * 128 + row) * 4 + half * 2);
-              if (xl2) {
-                // B3 takes its A operand (the dE/dx tile) from shared memory: nothing to build here.  This arrive
-                // only tells the issuer that the chain's accumulator columns are free (all tcgen05.ld of the
-                // previous item are complete in program order).
-                tc_fence_before();
-                ARR(); group_arrive(&a_ready[chain_id], lane);
-              } else {
-                // G = dE/dx_k (this point), columns xc0 .. xc0+31 -> X[xc0 : xc0+32]
+            // G = dE/dx_k of a row, columns xc0 .. xc0+31, packed for B3 and stored to tensor memory.  Single-term fp16
+            // backward (G_AHEAD): G lives in X[64:96], which no other backward operand or accumulator touches, so the
+            // NEXT item's rows are built and stored while B2 of the current item runs -- no registers are held across the
+            // epilogue phases (the 3-term format needs X[64:128] for residual operands and builds G in place, X[0:32]).
+            constexpr bool G_AHEAD = F16 && !X3B && !xl2 && VLG_TC_G_AHEAD;
+            const uint32_t gcolX = colX + (G_AHEAD ? 64u : 0u);
+            auto build_g = [&](int k, int pt, bool active, bool wact) {
                 if (wact) {
                   float g[32];
   #pragma unroll
@@ -1353,7 +1340,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                       else
                         v[j] = pack_h2(g0, g1);
                     }
-                    tmem_st16(colX + half * 16, v);
+                    tmem_st16(gcolX + half * 16, v);
                     if (X3B) tmem_st16(colX + 64 + half * 16, reinterpret_cast<uint32_t(&)[16]>(vl));
                   } else {
                     uint32_t v[32];
@@ -1362,9 +1349,52 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                     tmem_st32(colX + xc0, v);
                   }
                 }
-                tmem_wait_st();
+            };
+            int pend_pt = -1, pend_slot = 0;
+            // row of this thread in item `it2` (decoder, point, flags) -- for the look-ahead build
+            auto item_row = [&](int it2, int& k2, int& pt2, bool& act2, bool& wact2) {
+              k2 = ctl->item[it2] & 0xFF;
+              const int q02 = (ctl->item[it2] >> 8) * 128;
+              act2 = q02 + row < s.cnt[k2];
+              wact2 = q02 + (warp & 3) * 32 < s.cnt[k2];
+              pt2 = act2 ? s.rows[s.roff[k2] + q02 + row] : 0;
+            };
+            if (G_AHEAD && chain_id < nitems) {   // the first item of the chain
+              int k2, pt2; bool a2, w2;
+              item_row(chain_id, k2, pt2, a2, w2);
+              build_g(k2, pt2, a2, w2);
+              tmem_wait_st();
+              tc_fence_before();
+              ARR(); group_arrive(&a_ready[chain_id], lane);
+            }
+            for (int it = chain_id; it < nitems; it += 2) {
+              const int k = ctl->item[it] & 0xFF, q0 = (ctl->item[it] >> 8) * 128;
+              const bool active = q0 + row < s.cnt[k];
+              const bool wact = q0 + (warp & 3) * 32 < s.cnt[k];
+              const int pt = active ? s.rows[s.roff[k] + q0 + row] : 0;
+              mbar_wait(&sw_full[chain_id * SW_SLOTS + (swj % SW_SLOTS)], (swj / SW_SLOTS) & 1u);
+              if (!F16) named_bar(bar_id, GROUP_THREADS);
+              const float* sw = swbuf + (swj % SW_SLOTS) * 576;
+              ++swj;
+              const float2 z = s.zs[pt];
+              const float2 zx2 = make_float2(z.x, z.x), zy2 = make_float2(z.y, z.y);
+              // mask words for E-B3 (the L2 round trip overlaps the first MMA)
+              uint2 bits = make_uint2(0u, 0u);
+              if (active) bits = *reinterpret_cast<const uint2*>(maskws + (it * 128 + row) * 4 + half * 2);
+              if (xl2) {
+                // B3 takes its A operand (the dE/dx tile) from shared memory: nothing to build here.  This arrive
+                // only tells the issuer that the chain's accumulator columns are free (all tcgen05.ld of the
+                // previous item are complete in program order).
                 tc_fence_before();
                 ARR(); group_arrive(&a_ready[chain_id], lane);
+              } else {
+                // G = dE/dx_k (this point), columns xc0 .. xc0+31 -> tensor memory (see build_g)
+                if (!G_AHEAD) {
+                  build_g(k, pt, active, wact);
+                  tmem_wait_st();
+                  tc_fence_before();
+                  ARR(); group_arrive(&a_ready[chain_id], lane);
+                }
               }
               PH(9);
               // dh2 = (G W3) * mask2 -> A4 (Y, in place)
@@ -1412,6 +1442,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
               tc_fence_before();
               ARR(); group_arrive(&a_ready[chain_id], lane);
               PH(11);
+              if (G_AHEAD && it + 2 < nitems) {   // under B2 of this item: the next item's dE/dx rows -> X[64:96]
+                int k2, pt2; bool a2, w2;
+                item_row(it + 2, k2, pt2, a2, w2);
+                build_g(k2, pt2, a2, w2);
+                tmem_wait_st();
+              }
               // dh1 = (dh2 W2) * mask1 (recomputed); dz[point] += dh1 W1 over this thread's 64 hidden units
               { STAT_T0(); acc_wait(&acc_ready[chain_id], ph_acc, lane); STAT_ADD(w_acc); }
               ph_acc ^= 1;
@@ -1453,6 +1489,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                 pend_slot = (__ffs(int(slot_match(s.sel, pt, k))) - 1) >> 3;   // first draw slot of the point that holds decoder k
               }
               PH(13);
+              if (G_AHEAD && it + 2 < nitems) {   // D5 is in registers (tcgen05.wait::ld): B3 of the next item may overwrite Y
+                tc_fence_before();
+                ARR(); group_arrive(&a_ready[chain_id], lane);
+              }
             }
             named_bar(3, EPI_THREADS);
             PH(14);
