@@ -98,13 +98,10 @@ using namespace tc;
 #ifndef VLG_TC_G_AHEAD
 #define VLG_TC_G_AHEAD 1               // single-term backward: next item's dE/dx rows built under the current B2
 #endif
-#ifndef VLG_TC_DUAL_ISSUE
-#define VLG_TC_DUAL_ISSUE 0           // 1: one MMA issuer warp per chain (see the issuer)
-#endif
-constexpr int TC_THREADS = VLG_TC_DUAL_ISSUE ? 640 : 608;   // 3 (4) control warps + 16 epilogue warps
+constexpr int TC_THREADS = 608;       // 3 control warps + 16 epilogue warps
 constexpr int GROUP_THREADS = 256;    // one epilogue group (chain)
 constexpr int EPI_THREADS = 512;
-constexpr int FIRST_EPI_WARP = VLG_TC_DUAL_ISSUE ? 4 : 3;
+constexpr int FIRST_EPI_WARP = 3;
 constexpr int STAGE_BYTES = 16384;
 constexpr int MAX_STAGES = 5;         // per chain
 constexpr int XD_STRIDE = 52;         // floats per stored decoder output row (X <= 52; 16 B rows)
@@ -160,18 +157,7 @@ __device__ __forceinline__ OpInfo op_info(int op) {
 // hi / lo fp16 pairs of two fp32 values: hi = fp16(v), lo = fp16(v - hi).  The residual v - hi is exact in fp32 and
 // comes from one mixed-precision FMA per element (fma.rn.f32.f16: hi * -1 + v, SASS FHFMA) instead of a convert back
 // and a subtract -- 4 instructions per pair instead of 6, same bits.
-#ifndef VLG_OPT_FHFMA
-#define VLG_OPT_FHFMA 1
-#endif
 __device__ __forceinline__ void pack_hilo_h2(float a, float b, uint32_t& hi, uint32_t& lo) {
-#if !VLG_OPT_FHFMA
-  const __half2 h = __floats2half2_rn(a, b);
-  const float2 back = __half22float2(h);
-  const __half2 l = __floats2half2_rn(a - back.x, b - back.y);
-  hi = *reinterpret_cast<const uint32_t*>(&h);
-  lo = *reinterpret_cast<const uint32_t*>(&l);
-  return;
-#endif
   float ra, rb;
   asm("{\n\t.reg .b16 l, u, m1;\n\t"
       "cvt.rn.f16x2.f32 %0, %4, %3;\n\t"
@@ -188,19 +174,11 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   const __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&h);
 }
-#ifndef VLG_OPT_CVTRELU
-#define VLG_OPT_CVTRELU 1
-#endif
 __device__ __forceinline__ uint32_t pack_relu_h2(float a, float b) {
-#if VLG_OPT_CVTRELU
   // one instruction: round-to-nearest convert of both values with the ReLU clamp built in
   uint32_t r;
   asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
   return r;
-#else
-  const __half2 h = __hmax2(__floats2half2_rn(a, b), __float2half2_rn(0.f));
-  return *reinterpret_cast<const uint32_t*>(&h);
-#endif
 }
 // 0xFFFF in every 16-bit half of `w` that holds a positive fp16 value (one HSET2.BM)
 __device__ __forceinline__ uint32_t pos_mask_h2(uint32_t w) {
@@ -209,9 +187,6 @@ __device__ __forceinline__ uint32_t pos_mask_h2(uint32_t w) {
 // ReLU-mask word layouts.  MASKH (fp16 single-term kernel only): pair p = elements (2p, 2p+1) of a 32-column
 // tile -> bits p and 16+p, taken straight from the packed fp16 activations (HSET2 + LOP3 per pair instead of
 // 2 x (FSETP + LOP)); expanded in the backward pass to 16-bit lane masks with one IMAD.
-#ifndef VLG_OPT_MASKH
-#define VLG_OPT_MASKH 1
-#endif
 // Backward quantities (dE/dx and the hidden-layer gradients) are scaled by 2^6 before they are rounded to
 // fp16 and unscaled in fp32 when dz is accumulated: gradients of a converged curve are O(1e-2 .. 1e-5)
 // per element, fp16 loses precision below 6e-5.
@@ -230,17 +205,9 @@ __device__ __forceinline__ uint32_t slot_match(const uint8_t* sel, int pt, int k
 }
 // "operand ready" of an epilogue group: every thread has completed and fenced its tensor-memory stores; one arrival
 // per warp (the mbarrier counts the group's 8 warps) instead of 256 serialized arrivals on one shared-memory word
-#ifndef VLG_TC_WARP_ARRIVE
-#define VLG_TC_WARP_ARRIVE 1
-#endif
 __device__ __forceinline__ void group_arrive(uint64_t* bar, int lane) {
-#if VLG_TC_WARP_ARRIVE
   __syncwarp();
   if (lane == 0) mbar_arrive(bar);
-#else
-  (void)lane;
-  mbar_arrive(bar);
-#endif
 }
 __device__ __forceinline__ void named_bar(int id, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
@@ -283,19 +250,10 @@ struct WinCtl {
   uint16_t item[MAX_ITEMS];  // decoder | pass << 8
 };
 
-// Wait for the chain's accumulator.  VLG_TC_WAIT_MODE 0: every lane polls the mbarrier; 1: lane 0
-// polls and the warp reconverges on __syncwarp (32x fewer mbarrier probes in the memory queue).
-#ifndef VLG_TC_WAIT_MODE
-#define VLG_TC_WAIT_MODE 0
-#endif
+// Wait for the chain's accumulator: every lane polls the mbarrier (lane 0 polling + __syncwarp: measured -5 %).
 __device__ __forceinline__ void acc_wait(uint64_t* bar, uint32_t parity, int lane) {
-#if VLG_TC_WAIT_MODE == 1
-  if (lane == 0) mbar_wait(bar, parity);
-  __syncwarp();
-#else
   (void)lane;
   mbar_wait(bar, parity);
-#endif
 }
 
 struct TcSmem {
@@ -408,7 +366,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
   constexpr bool F16 = FMT != FMT_TF32;   // fp16 operands (one or two terms)
   constexpr bool X3F = FMT == FMT_F16X3 || FMT == FMT_F16X3F;   // 3-term split in the forward GEMMs (F2, F3)
   constexpr bool X3B = FMT == FMT_F16X3;                        // ... and in the backward GEMMs (B3, B2)
-  constexpr bool DUAL_ISSUE = VLG_TC_DUAL_ISSUE != 0;   // one MMA issuer warp per chain
   extern __shared__ __align__(128) unsigned char smem_raw[];
 #ifdef VLG_TC_STATS
   __shared__ volatile long long arr_t_[16];
@@ -443,8 +400,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
     }
-    mbar_init(&a_ready[0], VLG_TC_WARP_ARRIVE ? GROUP_THREADS / 32 : GROUP_THREADS);
-    mbar_init(&a_ready[1], VLG_TC_WARP_ARRIVE ? GROUP_THREADS / 32 : GROUP_THREADS);
+    mbar_init(&a_ready[0], GROUP_THREADS / 32);   // one arrival per epilogue warp (group_arrive)
+    mbar_init(&a_ready[1], GROUP_THREADS / 32);
     mbar_init(&acc_ready[0], 1);
     mbar_init(&acc_ready[1], 1);
     mbar_init(win_ready, 1);
@@ -545,35 +502,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
         mbar_arrive(&ctl_free[w & 1]);   // done reading this window's item list
       }
     }
-  } else if (warp < FIRST_EPI_WARP) {
-    // ================= MMA issuer(s) =================
-    // The whole warp runs this loop convergently; one elected lane's tcgen05 instructions take effect.
-    // DUAL_ISSUE = false: warp 2 serves whichever chain is ready (warp 3 idles); true: warp 2 + c serves chain c only.
-    // Two issuers interleave the chains' MMAs in the tensor pipe ("processor sharing": both GEMMs finish late) where
-    // one issuer runs them first come first served; measured: no gain in the 3-term mode, -2 % with single-term fp16
-    // operands (a fifth warp on one scheduler) -- off by default.
-    if (DUAL_ISSUE || warp == 2) {
-      const int c_lo = DUAL_ISSUE ? warp - 2 : 0, c_hi = DUAL_ISSUE ? warp - 1 : 2;
+  } else if (warp == 2) {
+    // ================= MMA issuer: serves whichever chain is ready =================
+    // The whole warp runs this loop convergently; one elected lane's tcgen05 instructions take effect.  (A second
+    // issuer warp -- one per chain -- interleaves the chains' MMAs in the tensor pipe, "processor sharing": both
+    // GEMMs finish late, and puts a fifth warp on one scheduler: measured no gain to -5 %)
+    {
       const uint32_t leader = elect_one();
       int slot[2] = {0, 0}, opi[2] = {0, 0}, nitc[2] = {0, 0};
       int ops_left[2] = {0, 0};      // ops of the chain's current window still to issue
       long win[2] = {0, 0};          // next window whose item list the chain has to pick up
-      bool fin[2] = {c_lo > 0, c_hi < 2};
+      bool fin[2] = {false, false};
       uint32_t ph[2] = {0, 0}, ph_a[2] = {0, 0};
       long long w_full = 0, w_issue = 0;
       STAT_T0();
-#ifndef VLG_TC_IDLE_NS
-#define VLG_TC_IDLE_NS 0
-#endif
       bool served = true;
       while (!(fin[0] && fin[1])) {
-        // back off when nothing was ready: a tight mbarrier.test_wait loop floods the SM's memory
-        // instruction queue and throttles the epilogue warps' loads (seen as lg/mio stalls in ncu)
-        if (!served && VLG_TC_IDLE_NS > 0) __nanosleep(VLG_TC_IDLE_NS);
+        // (backing off with __nanosleep when nothing was ready: measured -1 % at 64 ns, -2 % at 200 ns)
         served = false;
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-          if (fin[c]) continue;   // (also: a chain another issuer serves)
+          if (fin[c]) continue;
           if (ops_left[c] == 0) {
             if (!mbar_test(win_ready, uint32_t(win[c] & 1))) continue;
             const int nit = s.ctl[win[c] & 1].nitems;
@@ -676,7 +625,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
         }
       }
 #ifdef VLG_TC_STATS
-      if (lane == 0 && blockIdx.x < 1024 && warp == 2) {
+      if (lane == 0 && blockIdx.x < 1024) {
         g_tc_stats[blockIdx.x * 8 + 2] = w_full;
         g_tc_stats[blockIdx.x * 8 + 3] = clock64() - _t0;
         g_tc_stats[blockIdx.x * 8 + 5] = w_issue;
@@ -1004,7 +953,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                   const float4 b0 = *reinterpret_cast<const float4*>(sw + OFF_B2 + col0 + 32 * hh + j);
                   const float2 p0 = __fadd2_rn(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), make_float2(b0.x, b0.y));
                   const float2 p1 = __fadd2_rn(make_float2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])), make_float2(b0.z, b0.w));
-                  if (!(VLG_OPT_MASKH && F16 && !X3F)) {
+                  if (!(F16 && !X3F)) {
                     if (p0.x > 0.f) bb |= 1u << j;
                     if (p0.y > 0.f) bb |= 2u << j;
                     if (p1.x > 0.f) bb |= 4u << j;
@@ -1019,7 +968,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                   } else if (F16) {
                     // pairs go to v[0:16] (slots j/2, j/2+1 <= j were consumed already)
                     const uint32_t a0 = pack_relu_h2(p0.x, p0.y), a1 = pack_relu_h2(p1.x, p1.y);
-                    if (VLG_OPT_MASKH) {
+                    {
                       bb |= pos_mask_h2(a0) & (0x00010001u << (j >> 1));
                       bb |= pos_mask_h2(a1) & (0x00010001u << ((j >> 1) + 1));
                     }
@@ -1416,7 +1365,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_curve_kernel(StepParams p, i
                     uint32_t vl[X3B ? 16 : 1];
 #pragma unroll
                     for (int j = 0; j < 32; j += 2) {
-                      if (VLG_OPT_MASKH && !X3F) {
+                      if (!X3F) {
                         // bits p, 16+p -> 0xFFFF lane masks (no carries: 1 * 0xFFFF, 0x10000 * 0xFFFF)
                         const uint32_t lanes = ((mb >> (j >> 1)) & 0x00010001u) * 0xFFFFu;
                         v[j >> 1] = pack_h2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])) & lanes;

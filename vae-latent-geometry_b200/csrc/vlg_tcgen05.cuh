@@ -32,30 +32,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// VLG_OPT_WAITHINT > 0: pass a suspend-time hint (ns) so a waiting thread sleeps in hardware instead of
-// re-issuing try_wait / branch pairs (39 % of the executed warp instructions in the round-1 profile)
-#ifndef VLG_OPT_WAITHINT
-#define VLG_OPT_WAITHINT 0
-#endif
-__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
-      : "memory");
-  return ok != 0;
-}
+// (a suspend-time hint on try_wait made no difference: polling only fills idle issue slots)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-#if VLG_OPT_WAITHINT > 0
-  while (!mbar_try_wait_hint(bar, parity, VLG_OPT_WAITHINT)) {
-  }
-#else
   while (!mbar_try_wait(bar, parity)) {
   }
-#endif
 }
 
 // ---- 1-D bulk copy global -> shared, completion on an mbarrier (TMA engine) ---------------
