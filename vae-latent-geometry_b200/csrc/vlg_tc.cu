@@ -136,6 +136,9 @@ constexpr int FMT_TF32 = 0, FMT_F16 = 1, FMT_F16X3 = 2, FMT_F16X3F = 3;   // X3F
 // (~21 significant bits); a product is evaluated as hi*hi + lo*hi + hi*lo in the fp32 accumulator -- three
 // times the MMAs of FMT_F16, fp32-grade results.  The residual operand sits 64 columns above the main one
 // (X[64:128]), so every accumulator -- D3 included -- goes to Y.
+// Mixed mode (FMT_F16X3F, the default arithmetic): the forward GEMMs as FMT_F16X3, the backward GEMMs as FMT_F16.
+// Single-term backward GEMMs leave X[64:128] idle, which is where the dE/dx operand of the chain's NEXT item is
+// stored while B2 of the current item still runs (G_AHEAD in the backward loop): B3 then reads X[64:96].
 template <int FMT>
 __device__ __forceinline__ OpInfo op_info(int op) {
   if (FMT != FMT_TF32) {
