@@ -728,6 +728,8 @@ def test_config3_final_lengths_against_reference_fp64(vlg, prec):
         8e-4 / 9.5e-4 there);
       * the fp32-grade modes (fp32 kernel, 3-term tensor-core split) are statistically the reference's own fp32:
         median <= 1e-5, no more curves beyond 1e-3 than the reference's fp32 has (+2), worst curve <= 2x its worst;
+      * the default arithmetic (f16x3f: 3-term forward GEMMs, single-term backward GEMMs) meets the same outlier
+        bars and 1e-3 on the unselected sample (measured 1.3e-4, the reference's own fp32: 1.0e-4), median <= 5e-5;
       * the single-term modes (fp16 / TF32 operands: 2.5e-4 per step) stay within 2 % everywhere, median <= 5e-4.
     The table is printed."""
     g = Hh.load("config3_synth_1000")
