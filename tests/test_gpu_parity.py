@@ -524,7 +524,7 @@ def test_config5_shape_k64_npoly8_t256(vlg):
     r = O.optimize_steps(g["a"].astype(np.float64), g["b"].astype(np.float64), g["omega_init"].astype(np.float64),
                          g["basis"].astype(np.float64), Hh.tgrid(T, np.float64), n_poly, Hh.decoder_list(W, K, np.float64), draws, S)
     out, fill = {}, {}
-    for prec in ("fp32", "tf32", "f16", "f16x3"):
+    for prec in ("fp32", "tf32", "f16", "f16x3", "f16x3f"):
         model = make_model(vlg, g)
         st = {}
         _, trace = vlg.optimize_splines(model, dec, t, S, M=M, seed=seed, curve_id0=id0, precision=prec, return_trace=True,
@@ -539,13 +539,16 @@ def test_config5_shape_k64_npoly8_t256(vlg):
         assert np.abs(out[tc][1] - r["omega"]).max() < 0.25 * S * 1e-3 + 1e-6
     assert np.abs(out["f16x3"][0] / r["energy"] - 1).max() < 1e-4              # the 3-term split meets the fp32 bound
     assert np.abs(out["f16x3"][1] - r["omega"]).max() < 2e-5
+    assert np.abs(out["f16x3f"][0][0] / r["energy"][0] - 1).max() < 1e-4       # default arithmetic: the energy of a given curve is fp32-grade,
+    assert np.abs(out["f16x3f"][0] / r["energy"] - 1).max() < 1e-3             # later steps see the 11-bit gradient operands
+    assert np.abs(out["f16x3f"][1] - r["omega"]).max() < 0.25 * S * 1e-3 + 1e-6
     # multi-curve windows: several whole curves share a window, so one decoder's rows fill its 128-row items
     # (a 256-point curve alone would leave them ~12 % full)
     print("item fill:", fill)
     assert all(f > 0.6 for f in fill.values()), fill
 
 
-@pytest.mark.parametrize("tc", ["f16", "f16x3", "tf32"])
+@pytest.mark.parametrize("tc", ["f16", "f16x3", "f16x3f", "tf32"])
 def test_multi_curve_windows_are_shard_independent(vlg, tc):
     """K = 64, T = 256: windows hold several whole curves, so WHICH curves share a window depends on where a
     shard starts.  Each (point, decoder) row's dz goes to its own draw-slot cell and the cells of a point are added in
@@ -633,8 +636,8 @@ def test_full_pair_list_sharding_and_modes_agree(vlg, prec):
         assert float((torch.sqrt(e_full / e_x3) - 1).abs().max()) < 2e-3
 
 
-@pytest.mark.parametrize("prec", ["fp32", "tf32", "f16", "f16x3"])
-@pytest.mark.parametrize("T,N,K,M,n_poly", [(513, 150, 7, 2, 4), (2000, 5, 10, 2, 4), (130, 3, 3, 1, 8)])
+@pytest.mark.parametrize("prec", ["fp32", "tf32", "f16", "f16x3", "f16x3f"])
+@pytest.mark.parametrize("T,N,K,M,n_poly", [(513, 150, 7, 2, 4), (2000, 5, 10, 2, 4), (130, 3, 3, 1, 8), (256, 20, 70, 3, 8)])
 def test_kernels_write_only_inside_their_buffers(vlg, prec, T, N, K, M, n_poly):
     """Guard bands: the workspace is handed over at exactly vlg_workspace_bytes, and it, the curve state and
     the outputs sit inside larger buffers filled with a pattern; nothing outside the declared extents may
